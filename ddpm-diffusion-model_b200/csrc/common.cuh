@@ -1,0 +1,136 @@
+// Shared device/host helpers for libddpm_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include "../../include/ddpm_b200.h"
+
+typedef __nv_bfloat16 bf16;
+
+extern int64_t g_ddpm_launches;  // counted by LAUNCH_OK (host side, single-threaded use)
+
+#define LAUNCH_OK()                                   \
+    do {                                              \
+        ++g_ddpm_launches;                            \
+        cudaError_t e__ = cudaGetLastError();         \
+        if (e__ != cudaSuccess) return (int)e__;      \
+    } while (0)
+
+#define CUDA_TRY(x)                                   \
+    do {                                              \
+        cudaError_t e__ = (x);                        \
+        if (e__ != cudaSuccess) return (int)e__;      \
+    } while (0)
+
+static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+template <typename T> struct Cvt;
+template <> struct Cvt<float> {
+    __device__ __forceinline__ static float ld(const float* p) { return *p; }
+    __device__ __forceinline__ static void st(float* p, float v) { *p = v; }
+};
+template <> struct Cvt<bf16> {
+    __device__ __forceinline__ static float ld(const bf16* p) { return __bfloat162float(*p); }
+    __device__ __forceinline__ static void st(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+template <typename T> __device__ __forceinline__ float ldf(const T* p) { return Cvt<T>::ld(p); }
+template <typename T> __device__ __forceinline__ void stf(T* p, float v) { Cvt<T>::st(p, v); }
+
+// 8-element (bf16) / 4-element (fp32) 16-byte vectors of activations
+template <typename T> struct Vec16;
+template <> struct Vec16<float> {
+    static constexpr int N = 4;
+    float v[4];
+    __device__ __forceinline__ void load(const float* p) {
+        float4 t = *reinterpret_cast<const float4*>(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    __device__ __forceinline__ void store(float* p) const {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+template <> struct Vec16<bf16> {
+    static constexpr int N = 8;
+    float v[8];
+    __device__ __forceinline__ void load(const bf16* p) {
+        uint4 t = *reinterpret_cast<const uint4*>(p);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float2 f = __bfloat1622float2(h[i]);
+            v[2 * i] = f.x; v[2 * i + 1] = f.y;
+        }
+    }
+    __device__ __forceinline__ void store(bf16* p) const {
+        uint4 t;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        *reinterpret_cast<uint4*>(p) = t;
+    }
+};
+
+__device__ __forceinline__ float silu_f(float z) { return z / (1.0f + __expf(-z)); }
+__device__ __forceinline__ float dsilu_f(float z) {
+    float s = 1.0f / (1.0f + __expf(-z));
+    return s * (1.0f + z * (1.0f - s));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// NHWC view addressing (see ddpm_b200.h)
+struct TV {
+    char* ptr;
+    int N, H, W, C, pitch, halo;
+    int Hp, Wp;
+    __host__ __device__ TV() {}
+    __host__ __device__ explicit TV(const ddpm_tensor& t)
+        : ptr((char*)t.ptr), N(t.N), H(t.H), W(t.W), C(t.C), pitch(t.pitch), halo(t.halo),
+          Hp(t.H + 2 * t.halo), Wp(t.W + 2 * t.halo) {}
+    __device__ __forceinline__ int64_t pix(int n, int y, int x) const {
+        return ((int64_t)(n * Hp + y + halo) * Wp + x + halo) * pitch;
+    }
+    template <typename T> __device__ __forceinline__ T* at(int n, int y, int x, int c = 0) const {
+        return reinterpret_cast<T*>(ptr) + pix(n, y, x) + c;
+    }
+};
+
+static inline bool tensor_ok(const ddpm_tensor* t) {
+    return t && t->ptr && t->N > 0 && t->H > 0 && t->W > 0 && t->C > 0 && t->pitch >= t->C &&
+           (t->halo == 0 || t->halo == 1);
+}
+
+// Philox4x32-10 counter RNG (dropout masks; recomputed in backward from the same counters)
+__device__ __forceinline__ uint4 philox4(uint32_t k0, uint32_t k1, uint4 c) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+        uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+        k0 += W0; k1 += W1;
+    }
+    return c;
+}
+// keep-mask for element index `e` (one Philox call covers 4 consecutive elements)
+__device__ __forceinline__ bool dropout_keep(const uint64_t* rng, uint32_t layer, uint64_t e, float p) {
+    uint64_t seed = rng[0], step = rng[1];
+    uint4 r = philox4((uint32_t)seed, (uint32_t)(seed >> 32),
+                      make_uint4((uint32_t)(e >> 2), (uint32_t)(e >> 34), (uint32_t)step, layer));
+    uint32_t w = (e & 3) == 0 ? r.x : (e & 3) == 1 ? r.y : (e & 3) == 2 ? r.z : r.w;
+    return (float)(w >> 8) * (1.0f / 16777216.0f) >= p;
+}

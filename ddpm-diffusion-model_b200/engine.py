@@ -1,0 +1,721 @@
+"""Host-side executor of the UNet hot path on the C ABI (libddpm_b200.so).
+
+Data layout in HBM
+  * activations: NHWC, element type bf16 (autocast) or fp32, every buffer carries a one-pixel zero
+    halo (`[N][H+2][W+2][pitch]`) that no kernel ever writes -> 3x3 convolutions need no bounds
+    logic on the tensor-core path and skip-concatenation is a channel slice of one wide buffer
+    (producers write at a channel offset; `torch.cat` of unet_backbone.py:206 disappears);
+  * parameters / gradients: fp32 in the reference's OIHW layout (state_dict compatible); packed
+    copies `[Cout][tap][Cin]` (fprop) and `[Cin][tap'][Cout]` (dgrad) in the activation dtype are
+    cached per parameter version;
+  * the time path (sinusoid -> MLP -> per-block time_proj) is fp32 `[B][C]`.
+
+The forward functions return `(out, saved)`; the hand-derived backward functions consume `saved`
+in reverse order.  Nothing here touches the oracle and nothing falls back to ATen math.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import Tensor as CT
+
+_TORCH = {_lib.F32: torch.float32, _lib.BF16: torch.bfloat16}
+_ESZ = {_lib.F32: 4, _lib.BF16: 2}
+
+
+# ----------------------------------------------------------------------------------------------
+# buffers
+# ----------------------------------------------------------------------------------------------
+class _Pool:
+    """Recycles halo-zeroed activation buffers per (device, dtype, shape).  A buffer's interior is
+    always fully overwritten by its producer and its halo is never written, so no memset is needed
+    after the first allocation."""
+
+    def __init__(self):
+        self.free: Dict[tuple, List[torch.Tensor]] = {}
+        self.enabled = True
+
+    def get(self, key, device):
+        lst = self.free.get(key)
+        if lst:
+            return lst.pop()
+        _, dt, shape = key
+        return torch.zeros(shape, dtype=dt, device=device)
+
+    def put(self, key, t):
+        if self.enabled:
+            self.free.setdefault(key, []).append(t)
+
+    def clear(self):
+        self.free.clear()
+
+
+POOL = _Pool()
+
+
+class _Buf:
+    __slots__ = ("t", "key")
+
+    def __init__(self, t, key):
+        self.t, self.key = t, key
+
+    def __del__(self):
+        if self.key is None:          # wrapped (non-pooled) tensor
+            return
+        try:
+            POOL.put(self.key, self.t)
+        except Exception:
+            pass
+
+
+class Act:
+    """An NHWC view (possibly a channel slice) of a pooled buffer."""
+    __slots__ = ("buf", "N", "H", "W", "C", "pitch", "c0", "halo", "dt", "_d")
+
+    def __init__(self, buf, N, H, W, C, pitch, c0, halo, dt):
+        self.buf, self.N, self.H, self.W, self.C = buf, N, H, W, C
+        self.pitch, self.c0, self.halo, self.dt = pitch, c0, halo, dt
+        self._d = None
+
+    @staticmethod
+    def new(N, H, W, C, dt, device, halo=1) -> "Act":
+        shape = (N, H + 2 * halo, W + 2 * halo, C)
+        key = (str(device), _TORCH[dt], shape)
+        return Act(_Buf(POOL.get(key, device), key), N, H, W, C, C, 0, halo, dt)
+
+    @staticmethod
+    def wrap(t: torch.Tensor, N, H, W, C, dt, halo=0) -> "Act":
+        """View an existing contiguous tensor [N,H,W,C] (no pooling)."""
+        b = _Buf.__new__(_Buf)
+        b.t, b.key = t, None
+        a = Act(b, N, H, W, C, C, 0, halo, dt)
+        return a
+
+    def slice(self, c0, C) -> "Act":
+        return Act(self.buf, self.N, self.H, self.W, C, self.pitch, self.c0 + c0, self.halo, self.dt)
+
+    @property
+    def ptr(self) -> int:
+        return self.buf.t.data_ptr() + self.c0 * _ESZ[self.dt]
+
+    def desc(self) -> CT:
+        if self._d is None:
+            self._d = CT(self.ptr, self.N, self.H, self.W, self.C, self.pitch, self.halo)
+        return self._d
+
+    def interior(self) -> torch.Tensor:
+        """torch view [N,H,W,C] (debug / tests)."""
+        h = self.halo
+        t = self.buf.t
+        return t[:, h:t.shape[1] - h, h:t.shape[2] - h, self.c0:self.c0 + self.C]
+
+
+def _null_tensor() -> CT:
+    return CT(None, 0, 0, 0, 0, 0, 0)
+
+
+_NULL = _null_tensor()
+
+
+# ----------------------------------------------------------------------------------------------
+# per-call execution context
+# ----------------------------------------------------------------------------------------------
+class WeightCache:
+    """Packed (fprop / dgrad) copies of conv and linear weights, keyed by parameter identity and
+    refreshed when the parameter's version counter or the owner's epoch changes."""
+
+    def __init__(self):
+        self.entries: Dict[tuple, tuple] = {}
+        self.epoch = 0
+
+    def bump(self):
+        self.epoch += 1
+
+    def get(self, E: "Exec", w: torch.Tensor, dt: int, need_dgrad: bool):
+        key = (id(w), dt)
+        ent = self.entries.get(key)
+        stamp = (w._version, self.epoch, w.data_ptr())
+        if ent is not None and ent[0] == stamp and (ent[2] is not None or not need_dgrad):
+            return ent[1], ent[2]
+        co, ci = w.shape[0], w.shape[1]
+        kh, kw = (w.shape[2], w.shape[3]) if w.dim() == 4 else (1, 1)
+        tdt = _TORCH[dt]
+        fwd = ent[1] if ent is not None and ent[1] is not None else torch.empty(co * ci * kh * kw, dtype=tdt, device=w.device)
+        dg = None
+        if need_dgrad:
+            dg = ent[2] if ent is not None and ent[2] is not None else torch.empty(co * ci * kh * kw, dtype=tdt, device=w.device)
+        wd = w.detach()
+        if not wd.is_contiguous():
+            wd = wd.contiguous()
+        _lib.call("ddpm_pack_weights", wd.data_ptr(), co, ci, kh, kw, fwd.data_ptr(),
+                  dg.data_ptr() if dg is not None else None, dt, E.stream)
+        self.entries[key] = (stamp, fwd, dg, wd)
+        return fwd, dg
+
+
+GLOBAL_WCACHE = WeightCache()
+
+
+class Exec:
+    """Everything one forward(+backward) needs: dtype, stream, RNG state, weight cache, flags."""
+
+    def __init__(self, device, dt: int, training: bool, need_grad: bool, wcache: Optional[WeightCache] = None,
+                 rng: Optional[torch.Tensor] = None, prefer_tc: bool = True):
+        self.device = device
+        self.dt = dt
+        self.tdt = _TORCH[dt]
+        self.training = training
+        self.need_grad = need_grad
+        self.wcache = wcache if wcache is not None else GLOBAL_WCACHE
+        self.rng = rng
+        self.prefer_tc = 1 if prefer_tc else 0
+        self.stream = torch.cuda.current_stream(device).cuda_stream
+
+    # ---- allocation helpers
+    def act(self, N, H, W, C, halo=1) -> Act:
+        return Act.new(N, H, W, C, self.dt, self.device, halo)
+
+    def f32(self, *shape) -> torch.Tensor:
+        return torch.empty(shape, dtype=torch.float32, device=self.device)
+
+    def vec(self, t: torch.Tensor, B: int, Cn: int) -> Act:
+        """fp32 [B][C] tensor as an H=W=1 activation (time path)."""
+        return Act.wrap(t, B, 1, 1, Cn, _lib.F32, 0)
+
+
+def grad_of(p: torch.nn.Parameter) -> Optional[torch.Tensor]:
+    """fp32 gradient buffer of a parameter (created zeroed on first use; kernels accumulate)."""
+    if not p.requires_grad:
+        return None
+    if p.grad is None:
+        p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
+    return p.grad
+
+
+def _gptr(p) -> Optional[int]:
+    g = grad_of(p) if p is not None else None
+    return g.data_ptr() if g is not None else None
+
+
+# ----------------------------------------------------------------------------------------------
+# primitive ops (one C-ABI call each)
+# ----------------------------------------------------------------------------------------------
+def conv(E: Exec, x: Act, wpack: torch.Tensor, out: Act, k: int, stride: int = 1, pad: int = 0, *,
+         bias: Optional[torch.Tensor] = None, tbias: Optional[torch.Tensor] = None, res: Optional[Act] = None,
+         z: Optional[Act] = None, accum: bool = False, a_silu: bool = False, mode: int = _lib.CONV_NORMAL,
+         dt: Optional[int] = None) -> Act:
+    dt = x.dt if dt is None else dt
+    a = _lib.ConvArgs()
+    a.inp, a.out = x.desc(), out.desc()
+    a.w = wpack.data_ptr()
+    a.bias = bias.data_ptr() if bias is not None else None
+    if tbias is not None:
+        a.tbias, a.tbias_pitch = tbias.data_ptr(), tbias.stride(0)
+    else:
+        a.tbias, a.tbias_pitch = None, 0
+    a.res = res.desc() if res is not None else _NULL
+    a.z = z.desc() if z is not None else _NULL
+    a.KH = a.KW = k
+    a.stride, a.pad, a.mode = stride, pad, mode
+    a.a_silu = 1 if a_silu else 0
+    a.epi = (_lib.EPI_ACCUM if accum else 0) | (_lib.EPI_DSILU if z is not None else 0)
+    a.dtype = dt
+    a.prefer_tc = E.prefer_tc
+    _lib.call("ddpm_conv", C.byref(a), E.stream)
+    return out
+
+
+def wgrad(E: Exec, act: Act, dy: Act, w: torch.nn.Parameter, k: int, stride: int = 1, pad: int = 0,
+          a_silu: bool = False) -> None:
+    g = grad_of(w)
+    if g is None:
+        return
+    a = _lib.WgradArgs()
+    a.act, a.dy = act.desc(), dy.desc()
+    a.dw = g.data_ptr()
+    a.KH = a.KW = k
+    a.stride, a.pad = stride, pad
+    a.a_silu = 1 if a_silu else 0
+    a.dtype = act.dt
+    a.prefer_tc = E.prefer_tc
+    _lib.call("ddpm_conv_wgrad", C.byref(a), E.stream)
+
+
+def colsum(E: Exec, dy: Act, out_nc: Optional[torch.Tensor], bias: Optional[torch.nn.Parameter]) -> None:
+    gb = _gptr(bias)
+    if out_nc is None and gb is None:
+        return
+    _lib.call("ddpm_colsum", C.byref(dy.desc()), dy.dt, out_nc.data_ptr() if out_nc is not None else None, gb, E.stream)
+
+
+def gn_stats(E: Exec, x: Act, groups: int) -> torch.Tensor:
+    st = torch.empty((x.N, groups, 2), dtype=torch.float64, device=E.device)
+    _lib.call("ddpm_gn_stats", C.byref(x.desc()), x.dt, groups, st.data_ptr(), E.stream)
+    return st
+
+
+def gn_apply(E: Exec, x: Act, st: torch.Tensor, gn: torch.nn.GroupNorm, act: int, p_drop: float, layer: int,
+             out: Optional[Act] = None) -> Act:
+    if out is None:
+        out = E.act(x.N, x.H, x.W, x.C)
+    _lib.call("ddpm_gn_apply", C.byref(x.desc()), x.dt, gn.num_groups, st.data_ptr(), gn.weight.data_ptr(),
+              gn.bias.data_ptr(), float(gn.eps), act, float(p_drop), E.rng.data_ptr() if p_drop > 0 else None,
+              layer, C.byref(out.desc()), E.stream)
+    return out
+
+
+def gn_bwd(E: Exec, x: Act, st: torch.Tensor, gn: torch.nn.GroupNorm, act: int, p_drop: float, layer: int,
+           dy: Act, dx: Act, accumulate: bool) -> Act:
+    ws = E.f32(x.N, x.C, 2)
+    _lib.call("ddpm_gn_bwd", C.byref(x.desc()), x.dt, gn.num_groups, st.data_ptr(), gn.weight.data_ptr(),
+              gn.bias.data_ptr(), float(gn.eps), act, float(p_drop), E.rng.data_ptr() if p_drop > 0 else None,
+              layer, C.byref(dy.desc()), C.byref(dx.desc()), 1 if accumulate else 0, _gptr(gn.weight),
+              _gptr(gn.bias), ws.data_ptr(), E.stream)
+    return dx
+
+
+def add(E: Exec, a: Act, b: Act, out: Act) -> Act:
+    _lib.call("ddpm_add", C.byref(a.desc()), C.byref(b.desc()), C.byref(out.desc()), a.dt, E.stream)
+    return out
+
+
+def to_nhwc(E: Exec, x: torch.Tensor, halo=1) -> Act:
+    """NCHW-shaped torch tensor (any strides, fp32/bf16) -> pooled NHWC activation."""
+    B, Cc, H, W = x.shape
+    src_dt = _lib.F32 if x.dtype == torch.float32 else _lib.BF16
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.float()
+        src_dt = _lib.F32
+    out = E.act(B, H, W, Cc, halo)
+    sn, sc, sh, sw = x.stride()
+    _lib.call("ddpm_nchw_to_nhwc", x.data_ptr(), src_dt, sn, sc, sh, sw, C.byref(out.desc()), E.dt, E.stream)
+    return out
+
+
+def to_nchw(E: Exec, a: Act, out_dtype: torch.dtype) -> torch.Tensor:
+    out = torch.empty((a.N, a.C, a.H, a.W), dtype=out_dtype, device=E.device)
+    dd = _lib.F32 if out_dtype == torch.float32 else _lib.BF16
+    sn, sc, sh, sw = out.stride()
+    _lib.call("ddpm_nhwc_to_nchw", C.byref(a.desc()), a.dt, out.data_ptr(), dd, sn, sc, sh, sw, E.stream)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# linear layers of the time path (fp32, H=W=1)
+# ----------------------------------------------------------------------------------------------
+def linear_fwd(E: Exec, x: torch.Tensor, lin: torch.nn.Linear, a_silu: bool) -> torch.Tensor:
+    B = x.shape[0]
+    wf, _ = E.wcache.get(E, lin.weight, _lib.F32, False)
+    out = E.f32(B, lin.out_features)
+    conv(E, E.vec(x, B, lin.in_features), wf, E.vec(out, B, lin.out_features), 1, bias=lin.bias, a_silu=a_silu, dt=_lib.F32)
+    return out
+
+
+def linear_bwd(E: Exec, x: torch.Tensor, lin: torch.nn.Linear, a_silu: bool, dy: torch.Tensor,
+               dx: Optional[torch.Tensor], dx_accum: bool, need_dx: bool = True) -> Optional[torch.Tensor]:
+    """y = lin(silu?(x)).  Accumulates dW, db; returns d/dx (multiplied by silu'(x) when a_silu)."""
+    B = x.shape[0]
+    xa, dya = E.vec(x, B, lin.in_features), E.vec(dy, B, lin.out_features)
+    wgrad(E, xa, dya, lin.weight, 1, a_silu=a_silu)
+    if lin.bias is not None and lin.bias.requires_grad:
+        colsum(E, Act.wrap(dy, 1, 1, B, lin.out_features, _lib.F32, 0), None, lin.bias)
+    if not need_dx:
+        return None
+    _, wd = E.wcache.get(E, lin.weight, _lib.F32, True)
+    if dx is None:
+        dx = E.f32(B, lin.in_features)
+        dx_accum = False
+    conv(E, dya, wd, E.vec(dx, B, lin.in_features), 1, z=xa if a_silu else None, accum=dx_accum, dt=_lib.F32)
+    return dx
+
+
+# ----------------------------------------------------------------------------------------------
+# ResBlock  (unet_backbone.py:10-44)
+# ----------------------------------------------------------------------------------------------
+def resblock_fwd(E: Exec, blk, x: Act, tbias: torch.Tensor, out: Optional[Act] = None, layer: int = 0):
+    """h = conv1(silu(gn1(x))) + b1 + tbias ; out = conv2(drop(silu(gn2(h)))) + b2 + skip(x)."""
+    Cout = blk.out_ch
+    p_drop = float(blk.drop.p) if (E.training and isinstance(blk.drop, torch.nn.Dropout)) else 0.0
+    st1 = gn_stats(E, x, blk.norm1.num_groups)
+    a1 = gn_apply(E, x, st1, blk.norm1, 1, 0.0, 0)
+    w1, _ = E.wcache.get(E, blk.conv1.weight, E.dt, E.need_grad)
+    h = conv(E, a1, w1, E.act(x.N, x.H, x.W, Cout), 3, 1, 1, bias=blk.conv1.bias, tbias=tbias)
+    st2 = gn_stats(E, h, blk.norm2.num_groups)
+    a2 = gn_apply(E, h, st2, blk.norm2, 1, p_drop, layer)
+    w2, _ = E.wcache.get(E, blk.conv2.weight, E.dt, E.need_grad)
+    if out is None:
+        out = E.act(x.N, x.H, x.W, Cout)
+    if isinstance(blk.skip, torch.nn.Conv2d):
+        ws, _ = E.wcache.get(E, blk.skip.weight, E.dt, E.need_grad)
+        conv(E, x, ws, out, 1, bias=blk.skip.bias)
+        conv(E, a2, w2, out, 3, 1, 1, bias=blk.conv2.bias, accum=True)
+    else:
+        conv(E, a2, w2, out, 3, 1, 1, bias=blk.conv2.bias, res=x)
+    saved = (x, st1, a1, h, st2, a2, p_drop, layer) if E.need_grad else None
+    return out, saved
+
+
+def resblock_bwd(E: Exec, blk, saved, dout: Act, dx: Optional[Act] = None, dx_accum: bool = False):
+    """Returns (dx, dtbias [B][Cout] fp32).  `dout` may be overwritten (it becomes dx when the skip
+    is the identity and no explicit target is given)."""
+    x, st1, a1, h, st2, a2, p_drop, layer = saved
+    has_skip_conv = isinstance(blk.skip, torch.nn.Conv2d)
+    # conv2 (+ skip conv) parameter gradients
+    wgrad(E, a2, dout, blk.conv2.weight, 3, 1, 1)
+    colsum(E, dout, None, blk.conv2.bias)
+    _, w2d = E.wcache.get(E, blk.conv2.weight, E.dt, True)
+    da2 = conv(E, dout, w2d, E.act(x.N, x.H, x.W, blk.out_ch), 3, 1, 1)
+    dh = gn_bwd(E, h, st2, blk.norm2, 1, p_drop, layer, da2, da2, False)        # in place: dh overwrites da2
+    dtb = E.f32(x.N, blk.out_ch)
+    colsum(E, dh, dtb, blk.conv1.bias)
+    wgrad(E, a1, dh, blk.conv1.weight, 3, 1, 1)
+    _, w1d = E.wcache.get(E, blk.conv1.weight, E.dt, True)
+    da1 = conv(E, dh, w1d, E.act(x.N, x.H, x.W, blk.in_ch), 3, 1, 1)
+    if has_skip_conv:
+        wgrad(E, x, dout, blk.skip.weight, 1)
+        colsum(E, dout, None, blk.skip.bias)
+        _, wsd = E.wcache.get(E, blk.skip.weight, E.dt, True)
+        if dx is None:
+            dx, dx_accum = E.act(x.N, x.H, x.W, blk.in_ch), False
+        conv(E, dout, wsd, dx, 1, accum=dx_accum)
+        gn_bwd(E, x, st1, blk.norm1, 1, 0.0, 0, da1, dx, True)
+    else:
+        if dx is None:
+            dx = gn_bwd(E, x, st1, blk.norm1, 1, 0.0, 0, da1, dout, True)       # dout += gn_bwd -> dx
+        else:
+            gn_bwd(E, x, st1, blk.norm1, 1, 0.0, 0, da1, dx, dx_accum)
+            add(E, dx, dout, dx)
+    return dx, dtb
+
+
+# ----------------------------------------------------------------------------------------------
+# AttnBlock  (attention.py:42-74)
+# ----------------------------------------------------------------------------------------------
+def attn_fwd(E: Exec, blk, x: Act, out: Optional[Act] = None):
+    heads, d = blk.num_heads, blk.head_dim
+    inner = heads * d
+    st = gn_stats(E, x, blk.norm.num_groups)
+    a = gn_apply(E, x, st, blk.norm, 0, 0.0, 0)
+    wq, _ = E.wcache.get(E, blk.qkv.weight, E.dt, E.need_grad)
+    qkv = conv(E, a, wq, E.act(x.N, x.H, x.W, 3 * inner), 1)
+    o = E.act(x.N, x.H, x.W, inner)
+    lse = E.f32(x.N, heads, x.H * x.W)
+    _lib.call("ddpm_attn_fwd", C.byref(qkv.desc()), C.byref(o.desc()), heads, d, lse.data_ptr(), E.dt, E.stream)
+    wp, _ = E.wcache.get(E, blk.proj.weight, E.dt, E.need_grad)
+    if out is None:
+        out = E.act(x.N, x.H, x.W, x.C)
+    conv(E, o, wp, out, 1, bias=blk.proj.bias, res=x)
+    saved = (x, st, a, qkv, o, lse) if E.need_grad else None
+    return out, saved
+
+
+def attn_bwd(E: Exec, blk, saved, dout: Act, dx: Optional[Act] = None, dx_accum: bool = False) -> Act:
+    x, st, a, qkv, o, lse = saved
+    heads, d = blk.num_heads, blk.head_dim
+    inner = heads * d
+    n_tok = x.H * x.W
+    wgrad(E, o, dout, blk.proj.weight, 1)
+    colsum(E, dout, None, blk.proj.bias)
+    _, wpd = E.wcache.get(E, blk.proj.weight, E.dt, True)
+    do = conv(E, dout, wpd, E.act(x.N, x.H, x.W, inner), 1)
+    dqkv = E.act(x.N, x.H, x.W, 3 * inner)
+    scratch = E.f32(2, x.N, heads, n_tok, n_tok)
+    _lib.call("ddpm_attn_bwd", C.byref(qkv.desc()), C.byref(o.desc()), C.byref(do.desc()), lse.data_ptr(),
+              C.byref(dqkv.desc()), heads, d, scratch.data_ptr(), E.dt, E.stream)
+    wgrad(E, a, dqkv, blk.qkv.weight, 1)
+    _, wqd = E.wcache.get(E, blk.qkv.weight, E.dt, True)
+    da = conv(E, dqkv, wqd, E.act(x.N, x.H, x.W, x.C), 1)
+    if dx is None:
+        return gn_bwd(E, x, st, blk.norm, 0, 0.0, 0, da, dout, True)
+    gn_bwd(E, x, st, blk.norm, 0, 0.0, 0, da, dx, dx_accum)
+    return add(E, dx, dout, dx)
+
+
+# ----------------------------------------------------------------------------------------------
+# Downsample / Upsample  (unet_backbone.py:47-64)
+# ----------------------------------------------------------------------------------------------
+def down_fwd(E: Exec, mod, x: Act, out: Optional[Act] = None):
+    w, _ = E.wcache.get(E, mod.conv.weight, E.dt, E.need_grad)
+    Ho, Wo = (x.H - 1) // 2 + 1, (x.W - 1) // 2 + 1
+    if out is None:
+        out = E.act(x.N, Ho, Wo, x.C)
+    conv(E, x, w, out, 3, 2, 1, bias=mod.conv.bias)
+    return out, (x if E.need_grad else None)
+
+
+def down_bwd(E: Exec, mod, saved, dout: Act, dx: Optional[Act], dx_accum: bool) -> Act:
+    x = saved
+    wgrad(E, x, dout, mod.conv.weight, 3, 2, 1)
+    colsum(E, dout, None, mod.conv.bias)
+    _, wd = E.wcache.get(E, mod.conv.weight, E.dt, True)
+    if dx is None:
+        dx, dx_accum = E.act(x.N, x.H, x.W, x.C), False
+    conv(E, dout, wd, dx, 3, 2, 1, accum=dx_accum, mode=_lib.CONV_TRANSPOSED)
+    return dx
+
+
+def up_fwd(E: Exec, mod, x: Act, out: Optional[Act] = None):
+    u = E.act(x.N, 2 * x.H, 2 * x.W, x.C)
+    _lib.call("ddpm_upsample2x", C.byref(x.desc()), C.byref(u.desc()), E.dt, E.stream)
+    w, _ = E.wcache.get(E, mod.conv.weight, E.dt, E.need_grad)
+    if out is None:
+        out = E.act(x.N, u.H, u.W, x.C)
+    conv(E, u, w, out, 3, 1, 1, bias=mod.conv.bias)
+    return out, (u if E.need_grad else None)
+
+
+def up_bwd(E: Exec, mod, saved, dout: Act, dx: Optional[Act] = None, dx_accum: bool = False) -> Act:
+    u = saved
+    wgrad(E, u, dout, mod.conv.weight, 3, 1, 1)
+    colsum(E, dout, None, mod.conv.bias)
+    _, wd = E.wcache.get(E, mod.conv.weight, E.dt, True)
+    du = conv(E, dout, wd, E.act(u.N, u.H, u.W, u.C), 3, 1, 1)
+    if dx is None:
+        dx, dx_accum = E.act(u.N, u.H // 2, u.W // 2, u.C), False
+    _lib.call("ddpm_upsample2x_bwd", C.byref(du.desc()), C.byref(dx.desc()), E.dt, 1 if dx_accum else 0, E.stream)
+    return dx
+
+
+# ----------------------------------------------------------------------------------------------
+# time path  (attention.py:7-35, unet_backbone.py:25-27)
+# ----------------------------------------------------------------------------------------------
+def sinusoid(E: Exec, t: torch.Tensor, dim: int) -> torch.Tensor:
+    B = t.shape[0]
+    if t.dtype == torch.int64:
+        isf = 0
+    else:
+        t = t.float()
+        isf = 1
+    t = t.contiguous()
+    out = E.f32(B, dim)
+    _lib.call("ddpm_sinusoid", t.data_ptr(), isf, B, dim, out.data_ptr(), _lib.F32, E.stream)
+    return out
+
+
+def time_mlp_fwd(E: Exec, mlp, e0: torch.Tensor):
+    h1 = linear_fwd(E, e0, mlp.net[0], False)
+    temb = linear_fwd(E, h1, mlp.net[2], True)
+    return temb, ((e0, h1) if E.need_grad else None)
+
+
+def time_mlp_bwd(E: Exec, mlp, saved, dtemb: torch.Tensor, need_dx: bool = False):
+    e0, h1 = saved
+    dh1 = linear_bwd(E, h1, mlp.net[2], True, dtemb, None, False)
+    return linear_bwd(E, e0, mlp.net[0], False, dh1, None, False, need_dx=need_dx)
+
+
+# ----------------------------------------------------------------------------------------------
+# UNetDenoiser forward / backward  (unet_backbone.py:166-216)
+# ----------------------------------------------------------------------------------------------
+def _is_res(m) -> bool:
+    return hasattr(m, "conv1") and hasattr(m, "time_proj")
+
+
+def _is_attn(m) -> bool:
+    return hasattr(m, "qkv") and hasattr(m, "proj")
+
+
+def unet_resblocks(model) -> list:
+    """All ResBlocks in forward order (dropout layer ids / time_proj order)."""
+    out = []
+    for down in model.downs:
+        out += [b for b in down.blocks if _is_res(b)]
+    out += [b for b in model.mid if _is_res(b)]
+    for up in model.ups:
+        out += [b for b in up.blocks if _is_res(b)]
+    return out
+
+
+def unet_forward(E: Exec, model, x: torch.Tensor, t: torch.Tensor, out_dtype: torch.dtype):
+    """Returns (eps_pred NCHW tensor, saved-state for unet_backward or None)."""
+    B, Cin, H, W = x.shape
+    L = len(model.downs)
+    if H % (1 << (L - 1)) or W % (1 << (L - 1)):
+        raise NotImplementedError(
+            f"ddpm_b200 UNet needs H, W divisible by {1 << (L - 1)} (got {H}x{W}); the reference's "
+            "nearest-resize of mismatched skips (unet_backbone.py:202-203) is not implemented")
+    rbs = unet_resblocks(model)
+    rb_index = {id(b): i for i, b in enumerate(rbs)}
+    tape: list = []
+    G = E.need_grad
+
+    # ---- time path: temb, then one fp32 [B][Cout] bias per ResBlock
+    e0 = sinusoid(E, t, model.time_pos_emb.dim)
+    temb, mlp_saved = time_mlp_fwd(E, model.time_mlp, e0)
+    tbs = [linear_fwd(E, temb, b.time_proj[1], True) for b in rbs]
+
+    # ---- concat buffers, one per decoder level: [cur | skip]
+    enc_out_ch = []
+    for down in model.downs:
+        last = [b for b in down.blocks][-1]
+        enc_out_ch.append(last.out_ch if _is_res(last) else last.channels)
+    cats = []
+    for j, up in enumerate(model.ups):
+        lvl = L - 1 - j
+        first = up.blocks[0]
+        cat_c = first.in_ch
+        sk = enc_out_ch[lvl]
+        cats.append(E.act(B, H >> lvl, W >> lvl, cat_c))
+        assert cat_c - sk > 0
+    cur_ch_of = [cats[j].C - enc_out_ch[L - 1 - j] for j in range(L)]
+
+    # ---- encoder
+    x_in = to_nhwc(E, x)
+    w_in, _ = E.wcache.get(E, model.in_conv.weight, E.dt, False)
+    cur = conv(E, x_in, w_in, E.act(B, H, W, model.in_conv.out_channels), 3, 1, 1, bias=model.in_conv.bias)
+    if G:
+        tape.append(("in", x_in))
+    for li, down in enumerate(model.downs):
+        j = L - 1 - li
+        blocks = list(down.blocks)
+        for bi, blk in enumerate(blocks):
+            tgt = cats[j].slice(cur_ch_of[j], enc_out_ch[li]) if bi == len(blocks) - 1 else None
+            if _is_res(blk):
+                i = rb_index[id(blk)]
+                cur, sv = resblock_fwd(E, blk, cur, tbs[i], tgt, i + 1)
+                if G:
+                    tape.append(("res", blk, sv, i))
+            else:
+                cur, sv = attn_fwd(E, blk, cur, tgt)
+                if G:
+                    tape.append(("attn", blk, sv))
+        if G:
+            tape.append(("skip", j))
+        if not isinstance(down.down, torch.nn.Identity):
+            cur, sv = down_fwd(E, down.down, cur)
+            if G:
+                tape.append(("down", down.down, sv))
+
+    # ---- bottleneck
+    mids = [m for m in model.mid if not isinstance(m, torch.nn.Identity)]
+    for mi, blk in enumerate(mids):
+        tgt = cats[0].slice(0, cur_ch_of[0]) if (mi == len(mids) - 1 and isinstance(model.ups[0].up, torch.nn.Identity)) else None
+        if _is_res(blk):
+            i = rb_index[id(blk)]
+            cur, sv = resblock_fwd(E, blk, cur, tbs[i], tgt, i + 1)
+            if G:
+                tape.append(("res", blk, sv, i))
+        else:
+            cur, sv = attn_fwd(E, blk, cur, tgt)
+            if G:
+                tape.append(("attn", blk, sv))
+
+    # ---- decoder
+    for j, up in enumerate(model.ups):
+        if not isinstance(up.up, torch.nn.Identity):
+            cur, sv = up_fwd(E, up.up, cur, cats[j].slice(0, cur_ch_of[j]))
+            if G:
+                tape.append(("up", up.up, sv))
+        elif j != 0:
+            raise NotImplementedError("Identity up-sampler below the first decoder level")
+        cur = cats[j]
+        if G:
+            tape.append(("cat", j))
+        for blk in up.blocks:
+            i = rb_index[id(blk)]
+            cur, sv = resblock_fwd(E, blk, cur, tbs[i], None, i + 1)
+            if G:
+                tape.append(("res", blk, sv, i))
+
+    # ---- head
+    st = gn_stats(E, cur, model.out_norm.num_groups)
+    a = gn_apply(E, cur, st, model.out_norm, 1, 0.0, 0)
+    w_out, _ = E.wcache.get(E, model.out_conv.weight, E.dt, G)
+    y = conv(E, a, w_out, E.act(B, H, W, model.out_conv.out_channels), 3, 1, 1, bias=model.out_conv.bias)
+    out = to_nchw(E, y, out_dtype)
+    saved = None
+    if G:
+        saved = dict(tape=tape, head=(cur, st, a), temb=temb, mlp=mlp_saved, rbs=rbs, cats_shape=[(c.N, c.H, c.W, c.C) for c in cats],
+                     cur_ch_of=cur_ch_of, enc_out_ch=enc_out_ch, L=L, xshape=tuple(x.shape))
+    return out, saved
+
+
+def unet_backward(E: Exec, model, saved, dy: torch.Tensor, need_dx: bool, progress=None) -> Optional[torch.Tensor]:
+    """Accumulates every parameter gradient into `.grad`; returns d/dx (NCHW fp32) if requested.
+    `progress(module)` is called each time all gradients of a sub-module are final (used by the
+    data-parallel gradient buckets to overlap the all-reduce with the rest of backward)."""
+    if progress is None:
+        progress = getattr(model, "_ddpm_grad_progress", None)
+    tape = saved["tape"]
+    cur_h, st, a = saved["head"]
+    L = saved["L"]
+    B = saved["xshape"][0]
+    rbs = saved["rbs"]
+    dtemb: Optional[torch.Tensor] = None
+    temb = saved["temb"]
+
+    # ---- head
+    dyn = to_nhwc(E, dy)
+    wgrad(E, a, dyn, model.out_conv.weight, 3, 1, 1)
+    colsum(E, dyn, None, model.out_conv.bias)
+    _, wd = E.wcache.get(E, model.out_conv.weight, E.dt, True)
+    da = conv(E, dyn, wd, E.act(a.N, a.H, a.W, a.C), 3, 1, 1)
+    dcur = gn_bwd(E, cur_h, st, model.out_norm, 1, 0.0, 0, da, da, False)
+    del da, dyn
+    if progress is not None:
+        progress(model.out_conv)
+
+    dcats: List[Optional[Act]] = [None] * L
+    dx = None
+    for idx in range(len(tape) - 1, -1, -1):
+        ent = tape[idx]
+        kind = ent[0]
+        if kind == "res":
+            _, blk, sv, i = ent
+            dcur, dtb = resblock_bwd(E, blk, sv, dcur)
+            dtemb = linear_bwd(E, temb, blk.time_proj[1], True, dtb, dtemb, dtemb is not None)
+            if progress is not None:
+                progress(blk)
+        elif kind == "attn":
+            _, blk, sv = ent
+            dcur = attn_bwd(E, blk, sv, dcur)
+            if progress is not None:
+                progress(blk)
+        elif kind == "cat":
+            j = ent[1]
+            # dcur is the gradient of the whole [cur | skip] buffer
+            dcats[j] = dcur
+            dcur = dcur.slice(0, saved["cur_ch_of"][j])
+        elif kind == "up":
+            _, mod, sv = ent
+            dcur = up_bwd(E, mod, sv, dcur)
+            if progress is not None:
+                progress(mod)
+        elif kind == "down":
+            _, mod, sv = ent
+            # gradient of the level output = skip part of dcat (+)= dgrad of the stride-2 conv
+            assert tape[idx - 1][0] == "skip"
+            j = tape[idx - 1][1]        # decoder level fed by this encoder level's output
+            tgt = dcats[j].slice(saved["cur_ch_of"][j], saved["enc_out_ch"][L - 1 - j])
+            dcur = down_bwd(E, mod, sv, dcur, tgt, True)
+            if progress is not None:
+                progress(mod)
+        elif kind == "skip":
+            j = ent[1]
+            tgt = dcats[j].slice(saved["cur_ch_of"][j], saved["enc_out_ch"][L - 1 - j])
+            if not _same_view(dcur, tgt):
+                # last encoder level: its consumer was the bottleneck, whose dx is in `dcur`
+                dcur = add(E, dcur, tgt, tgt)
+        elif kind == "in":
+            x_in = ent[1]
+            wgrad(E, x_in, dcur, model.in_conv.weight, 3, 1, 1)
+            colsum(E, dcur, None, model.in_conv.bias)
+            if need_dx:
+                _, wdi = E.wcache.get(E, model.in_conv.weight, E.dt, True)
+                dxa = conv(E, dcur, wdi, E.act(x_in.N, x_in.H, x_in.W, x_in.C), 3, 1, 1)
+                dx = to_nchw(E, dxa, torch.float32)
+    # ---- time path (the per-block time_proj gradients were produced inside the loop)
+    if dtemb is not None:
+        time_mlp_bwd(E, model.time_mlp, saved["mlp"], dtemb)
+    if progress is not None:
+        progress(None)           # everything is final
+    return dx if need_dx else None
+
+
+def _same_view(a: Act, b: Act) -> bool:
+    return a.buf is b.buf and a.c0 == b.c0 and a.C == b.C
+

@@ -1,0 +1,239 @@
+"""Drop-in for src/training_loops/train_one_epoch.py (same signature and return value).
+
+What changes underneath: the UNet fwd/bwd run on libddpm_b200; parameters live in a
+flat arena; `scaler.unscale_ + clip_grad_norm_ + optimizer.step + scaler.update + ema.update`
+collapse into one reduction + one fused update kernel when the optimiser is torch Adam/AdamW; the
+per-micro-batch `float(loss)` host sync (train_one_epoch.py:119) becomes a device-side sum read once
+at the end; under torch.distributed the gradient arena is averaged bucket by bucket during backward.
+"""
+import ctypes as C
+import time
+
+import torch
+
+from .. import _lib
+from .. import dist as _dist
+from ..arena import ensure_arena
+from ..engine import GLOBAL_WCACHE
+from .ema import EMA  # noqa: F401
+from .grad_scaler import autocast_ctx, make_grad_scaler  # noqa: F401
+from .training_utils import compute_grad_norm, gpu_mem_mb
+
+
+def _stream(dev) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+class FusedStep:
+    """Owns the flat Adam moments / step counter and runs the fused optimiser-side pass."""
+
+    def __init__(self, model, optimizer, arena):
+        self.model, self.opt, self.arena = model, optimizer, arena
+        self.stats = torch.zeros(4, dtype=torch.float32, device=arena.flat.device)
+        self.fusable = self._fusable()
+        if self.fusable:
+            self._adopt_state()
+
+    def _fusable(self) -> bool:
+        opt = self.opt
+        if type(opt) not in (torch.optim.AdamW, torch.optim.Adam) or len(opt.param_groups) != 1:
+            return False
+        g = opt.param_groups[0]
+        if g.get("amsgrad") or g.get("maximize") or g.get("differentiable"):
+            return False
+        ps = g["params"]
+        return len(ps) == len(self.arena.params) and all(a is b for a, b in zip(ps, self.arena.params))
+
+    def _adopt_state(self):
+        ar, opt = self.arena, self.opt
+        self.m = torch.zeros_like(ar.flat)
+        self.v = torch.zeros_like(ar.flat)
+        self.step = torch.zeros(1, dtype=torch.float32, device=ar.flat.device)
+        mv, vv = ar.views(self.m), ar.views(self.v)
+        with torch.no_grad():
+            for p, a, b in zip(ar.params, mv, vv):
+                st = opt.state.get(p)
+                if st:                                    # resume: adopt existing moments
+                    a.copy_(st["exp_avg"])
+                    b.copy_(st["exp_avg_sq"])
+                    self.step.fill_(float(st["step"]))
+                opt.state[p] = {"step": self.step[0], "exp_avg": a, "exp_avg_sq": b}
+
+    def still_valid(self, model, optimizer, arena) -> bool:
+        return model is self.model and optimizer is self.opt and arena is self.arena and arena.valid()
+
+    def run(self, scaler, use_scaler: bool, grad_clip, ema):
+        ar = self.arena
+        dev = ar.flat.device
+        st = _stream(dev)
+        scale_ptr = scaler._scale.data_ptr() if use_scaler else None
+        _lib.call("ddpm_param_reduce", ar.grad.data_ptr(), ar.numel, self.stats.data_ptr(), st)
+        max_norm = float(grad_clip) if grad_clip is not None else 0.0
+        ema_flat = None
+        if ema is not None and isinstance(ema, EMA) and (ema._flat_ok(self.model) or ema._reflatten(self.model)):
+            ema_flat = ema._flat
+        if self.fusable:
+            g = self.opt.param_groups[0]
+            h = _lib.AdamHyper(float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
+                               float(g["weight_decay"]), max_norm, float(ema.decay) if ema_flat is not None else 0.0,
+                               1 if type(self.opt) is torch.optim.AdamW else 0)
+            _lib.call("ddpm_param_update", ar.flat.data_ptr(), ar.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                      ema_flat.data_ptr() if ema_flat is not None else None, ar.numel, self.stats.data_ptr(),
+                      self.step.data_ptr(), scale_ptr, C.byref(h), st)
+            if ema is not None and ema_flat is None:
+                ema.update(self.model)
+        else:
+            # any other optimiser: unscale+clip in one kernel, torch's own step, then the EMA kernel
+            _lib.call("ddpm_grad_unscale_clip", ar.grad.data_ptr(), ar.numel, self.stats.data_ptr(), scale_ptr, max_norm, st)
+            if float(self.stats[1].item()) == 0.0:
+                self.opt.step()
+            if ema is not None:
+                ema.update(self.model)
+        if use_scaler:
+            _lib.call("ddpm_scaler_update", scaler._scale.data_ptr(), scaler._growth_tracker.data_ptr(),
+                      self.stats.data_ptr(), float(scaler.get_growth_factor()), float(scaler.get_backoff_factor()),
+                      int(scaler.get_growth_interval()), st)
+        GLOBAL_WCACHE.bump()              # packed weight copies are stale now
+        ar.grad.zero_()                   # == optimizer.zero_grad(); grads stay attached (views)
+
+    def grad_norm(self, scaler, use_scaler: bool) -> float:
+        """||g||_2 of the unscaled gradients from the last reduction (diagnostic; one host sync)."""
+        s = float(scaler._scale.item()) if use_scaler else 1.0
+        return float(self.stats[0].item()) ** 0.5 / s
+
+
+def _get_fused(model, optimizer, arena) -> FusedStep:
+    fs = getattr(model, "_ddpm_fused_step", None)
+    if fs is None or not fs.still_valid(model, optimizer, arena):
+        fs = FusedStep(model, optimizer, arena)
+        object.__setattr__(model, "_ddpm_fused_step", fs)
+    return fs
+
+
+def _header(probe_timesteps):
+    print("┆   {:>8} | {:>9} | {:>8} | {:>8} | {:>10}{}".format(
+        "step", "lr", "loss", "dt(ms)", "grad_norm", (" | probes[t]" if probe_timesteps else "")))
+    print("┆   " + "─" * 72)
+
+
+def train_one_epoch(model, diffusion, dataloader, optimizer, *, scaler=None, ema=None, device: str = "cuda",
+                    max_batches: int | None = None, grad_clip: float | None = 1.0, use_autocast: bool = True,
+                    grad_accum_steps: int = 1, use_channels_last: bool = False, on_oom: str = "skip",
+                    base_lr: float | None = None, warmup_steps: int | None = None, global_step: int = 0,
+                    log_every: int = 0, probe_timesteps: list[int] | None = None, log_mem: bool = False,
+                    log_grad_norm: bool = False):
+    """train_one_epoch.py:11-168.  Returns (avg_loss, n_batches, n_images, global_step)."""
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("ddpm_b200.train_one_epoch is CUDA-only (sm_100a); there is no CPU fallback")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    model.train()
+    # use_channels_last only affects the *input* layout here: kernels are NHWC internally and the
+    # parameters must stay contiguous OIHW views of the flat arena.
+    rank, world = _dist.world()
+    verbose = rank == 0
+    grad_accum_steps = max(1, int(grad_accum_steps))
+    arena = ensure_arena(model)
+    if arena is None:
+        raise RuntimeError("ddpm_b200.train_one_epoch needs an fp32 CUDA model with all parameters trainable")
+    fused = _get_fused(model, optimizer, arena)
+    arena.attach_grads(zero=True)                      # == optimizer.zero_grad(set_to_none=True)
+    sync = _dist.attach_grad_sync(model, arena) if world > 1 else None
+    use_scaler = bool(use_autocast and (scaler is not None))
+
+    loss_sum = torch.zeros((), dtype=torch.float32, device=dev)
+    n_seen_batches, n_seen_images = 0, 0
+    did_header = False
+    if log_every and global_step == 0:
+        with torch.no_grad():
+            xb = torch.randn(32, 3, diffusion.img_size, diffusion.img_size, device=dev)
+            base = float((xb ** 2).mean().item())
+        if verbose:
+            print("┆ In-epoch statistics")
+            print("┆   (baseline)  ε-MSE ≈ {:.3f}  (esperado ~1.0)".format(base))
+            _header(probe_timesteps)
+        did_header = True
+
+    for i, (x, _) in enumerate(dataloader):
+        if (max_batches is not None) and (i >= max_batches):
+            break
+        try:
+            t_start = time.perf_counter()
+            x = x.to(dev, non_blocking=True)
+            if use_channels_last:
+                x = x.to(memory_format=torch.channels_last)
+            B = x.size(0)
+            t = diffusion.sample_timesteps(B, device=dev)
+            step_now = ((i + 1) % grad_accum_steps) == 0
+            if not arena.grads_attached():
+                arena.attach_grads(zero=True)
+            if sync is not None:
+                if step_now:
+                    sync.begin()
+                else:
+                    sync.reset()
+
+            with autocast_ctx(device="cuda", enabled=bool(use_autocast), dtype="bf16"):
+                loss = diffusion.loss_simple(model, x, t) / grad_accum_steps
+            if use_scaler:
+                scaler.scale(loss).backward()
+            else:
+                loss.backward()
+
+            gnorm = None
+            if step_now:
+                if (base_lr is not None) and (warmup_steps is not None) and (warmup_steps > 0):
+                    lr = base_lr * min(1.0, (global_step + 1) / warmup_steps)
+                    for g in optimizer.param_groups:
+                        g["lr"] = lr
+                if sync is not None:
+                    sync.finish()
+                fused.run(scaler if use_scaler else None, use_scaler, grad_clip, ema)
+                if log_grad_norm:
+                    gnorm = fused.grad_norm(scaler, use_scaler)
+                global_step += 1
+
+            loss_sum += loss.detach().float() * grad_accum_steps
+            n_seen_batches += 1
+            n_seen_images += B
+
+            if log_every and (global_step % log_every == 0) and step_now:
+                if not did_header:
+                    if verbose:
+                        print("┆ In-epoch statistics")
+                        _header(probe_timesteps)
+                    did_header = True
+                probe_msg = ""
+                if probe_timesteps:
+                    with torch.no_grad(), autocast_ctx(device="cuda", enabled=True, dtype="bf16"):
+                        vals = []
+                        for tau in probe_timesteps:
+                            t_fix = torch.full((B,), int(tau), device=dev, dtype=torch.long)
+                            vals.append(f"t={tau}:{diffusion.loss_simple(model, x, t_fix).item():.3f}")
+                        probe_msg = " | " + " ".join(vals)
+                mem_msg = ""
+                if log_mem:
+                    alloc, reserv = gpu_mem_mb("cuda")
+                    mem_msg = f" | mem={alloc:.0f}/{reserv:.0f}MB"
+                lr_now = optimizer.param_groups[0]["lr"]
+                dt = (time.perf_counter() - t_start) * 1000.0
+                gn_str = (f"{gnorm:.2e}" if (gnorm is not None) else "—")
+                loss_val = (loss.detach() * grad_accum_steps).item()
+                if verbose:
+                    print("┆   {:8d} | {:9.2e} | {:8.4f} | {:8.1f} | {:>10}{}{}".format(
+                        global_step, lr_now, loss_val, dt, gn_str, mem_msg, probe_msg))
+        except RuntimeError as e:
+            if ("CUDA out of memory" in str(e)) and (on_oom == "skip"):
+                import gc
+                gc.collect()
+                torch.cuda.empty_cache()
+                if verbose:
+                    print(f"[WARN][OOM] Batch {i} omitido. Limpié cache y sigo…")
+                if arena.grad is not None:
+                    arena.grad.zero_()
+                continue
+            raise
+
+    avg_loss = float(loss_sum.item()) / max(1, n_seen_batches)
+    return avg_loss, n_seen_batches, n_seen_images, global_step

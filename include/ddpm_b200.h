@@ -1,0 +1,196 @@
+/*
+ * ddpm_b200.h -- C ABI of libddpm_b200.so: the sm_100a CUDA implementation of the DDPM/DDIM hot
+ * path of pablo-reyes8/ddpm-diffusion-model.
+ *
+ * The reference is pure Python/PyTorch and has no FFI of its own; each entry point
+ * below cites the reference site (path:line under /root/reference) whose ATen work it replaces.
+ * INTEGRATION.md shows the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a positive cudaError_t, or a negative DDPM_E_* code;
+ *   - no allocation, no host synchronisation, no hidden state except the schedule handle;
+ *   - `stream` is a cudaStream_t passed as void*; all work is ordered on it (graph-capturable);
+ *   - activations are NHWC with an optional zero halo of one pixel (struct ddpm_tensor), element
+ *     type chosen by `dtype` (DDPM_F32 / DDPM_BF16); parameters and their gradients are fp32 in
+ *     the reference's OIHW / [out,in] layouts;
+ *   - kernels never write the halo, so a buffer whose halo was zeroed once stays valid.
+ */
+#ifndef DDPM_B200_H
+#define DDPM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DDPM_F32 0
+#define DDPM_BF16 1
+
+#define DDPM_E_ARG (-1)      /* invalid argument / unsupported shape */
+#define DDPM_E_NOTREADY (-2) /* schedule handle not initialised */
+
+/* NHWC view.  addr(n,y,x,c) = ptr + (((n*(H+2*halo) + y+halo)*(W+2*halo)) + x+halo)*pitch + c */
+typedef struct {
+    void* ptr;   /* element (n=0,y=-halo,x=-halo,c=0) of this view (channel offset folded in) */
+    int32_t N, H, W, C;
+    int32_t pitch; /* elements between consecutive pixels (>= C; > C for channel slices) */
+    int32_t halo;  /* 0 or 1 */
+} ddpm_tensor;
+
+int ddpm_abi_version(void);
+int ddpm_num_sms(int device, int* out);
+/* Returns and resets the count of kernels this library launched since the last call. */
+int64_t ddpm_launch_count(int reset);
+
+/* ---------------- schedule tables: difussion_class.py:46-68 (10 fp32 [T] buffers) ---------- */
+/* rows: 0 betas 1 alphas 2 alphas_cumprod 3 sqrt_ac 4 sqrt_1m_ac 5 ac_prev 6 post_var
+ *       7 post_logvar 8 post_coef1 9 post_coef2.   `tables_dev` is a device pointer [10][T]. */
+int ddpm_schedule_create(const float* tables_dev, int T, int device, void** handle);
+int ddpm_schedule_destroy(void* handle);
+
+/* ---------------- diffusion elementwise: difussion_class.py:81-234 ------------------------ */
+/* q_sample (:81-91).  x0, eps, xt: contiguous fp32 [B][chw]; t: int64 [B] (clamped to [0,T-1]). */
+int ddpm_q_sample(void* sched, const float* x0, const float* eps, const int64_t* t, float* xt,
+                  int B, int64_t chw, void* stream);
+/* loss_simple tail (:113-116).  loss[0] += mean_b(w_b * mean_chw((noise-pred)^2)); caller zeroes
+ * loss.  pred dtype f32/bf16, contiguous [B][chw].  weight may be NULL. */
+int ddpm_mse_fwd(const void* pred, int pred_dtype, const float* noise, const float* weight,
+                 float* loss, int B, int64_t chw, void* stream);
+/* d loss / d pred = 2 (pred-noise) w_b / (B*chw) * gout[0]; written in pred's dtype. */
+int ddpm_mse_bwd(const void* pred, int pred_dtype, const float* noise, const float* weight,
+                 const float* gout, void* dpred, int B, int64_t chw, void* stream);
+/* per-sample max|x0_hat| before thresholding (:143).  amax: fp32 [B], zeroed by the call. */
+int ddpm_x0_absmax(void* sched, const float* xt, const void* eps, int eps_dtype, const int64_t* t,
+                   float* amax, int B, int64_t chw, void* stream);
+/* flags for the sampler steps */
+#define DDPM_CLAMP_X0 1   /* clamp x0_hat to [-1,1] (:150-151, :179-180) */
+#define DDPM_DYN_THRESH 2 /* divide by max(amax,1).clamp(min=s) then clamp (:143-149) */
+/* p_sample_step (:156-187) given eps_pred.  noise may be NULL only if all t == 0. */
+int ddpm_p_sample_step(void* sched, const float* xt, const void* eps, int eps_dtype,
+                       const float* noise, const int64_t* t, const float* amax, float dyn_s,
+                       int flags, float* out, int B, int64_t chw, void* stream);
+/* p_sample_step_ddim (:189-234) given eps_pred.  noise may be NULL when eta == 0. */
+int ddpm_ddim_step(void* sched, const float* xt, const void* eps, int eps_dtype,
+                   const float* noise, const int64_t* t, const int64_t* t_prev, float eta,
+                   const float* amax, float dyn_s, int flags, float* out, int B, int64_t chw,
+                   void* stream);
+/* (clamp(x,-1,1)+1)/2: ddpm_inference.py:40, ddpim_inference.py:89 */
+int ddpm_to_image01(const float* x, float* out, int64_t n, void* stream);
+
+/* ---------------- layout at the API boundary (NCHW-shaped, any strides <-> NHWC) ---------- */
+int ddpm_nchw_to_nhwc(const void* src, int src_dtype, int64_t sn, int64_t sc, int64_t sh,
+                      int64_t sw, const ddpm_tensor* dst, int dst_dtype, void* stream);
+int ddpm_nhwc_to_nchw(const ddpm_tensor* src, int src_dtype, void* dst, int dst_dtype, int64_t sn,
+                      int64_t sc, int64_t sh, int64_t sw, void* stream);
+
+/* ---------------- time embedding: attention.py:13-22 -------------------------------------- */
+/* t: int64 or fp32 [B] (t_is_float); out: [B][dim] in `dtype`. */
+int ddpm_sinusoid(const void* t, int t_is_float, int B, int dim, void* out, int dtype, void* stream);
+
+/* ---------------- GroupNorm (+SiLU, +dropout): attention.py:38-39, unet_backbone.py:38,43 -- */
+/* stats: double [N][G][2] = (sum, sum of squares) over the group's elements; zeroed by the call. */
+int ddpm_gn_stats(const ddpm_tensor* x, int dtype, int groups, double* stats, void* stream);
+/* out = drop(act(gn(x))); act: 0 none, 1 SiLU.  rng: device uint64[2] {seed, step} (may be NULL
+ * when p_drop == 0); layer_id decorrelates call sites. */
+int ddpm_gn_apply(const ddpm_tensor* x, int dtype, int groups, const double* stats, const float* gamma,
+                  const float* beta, float eps, int act, float p_drop, const uint64_t* rng,
+                  uint32_t layer_id, const ddpm_tensor* out, void* stream);
+/* backward of gn_apply.  ws: fp32 [N][C][2] scratch (zeroed by the call).  dx (+)= ...;
+ * dgamma/dbeta (fp32 [C]) are accumulated. */
+int ddpm_gn_bwd(const ddpm_tensor* x, int dtype, int groups, const double* stats, const float* gamma,
+                const float* beta, float eps, int act, float p_drop, const uint64_t* rng,
+                uint32_t layer_id, const ddpm_tensor* dy, const ddpm_tensor* dx, int accumulate,
+                float* dgamma, float* dbeta, float* ws, void* stream);
+
+/* nearest x2 (unet_backbone.py:63) and its adjoint (2x2 sum) */
+int ddpm_upsample2x(const ddpm_tensor* x, const ddpm_tensor* out, int dtype, void* stream);
+int ddpm_upsample2x_bwd(const ddpm_tensor* dy, const ddpm_tensor* dx, int dtype, int accumulate, void* stream);
+/* out = a + b (all three may alias channel slices); used for gradient fan-in */
+int ddpm_add(const ddpm_tensor* a, const ddpm_tensor* b, const ddpm_tensor* out, int dtype, void* stream);
+/* out_nc[n][c] = sum_pixels dy (fp32, overwritten, may be NULL); dbias[c] += sum_n (may be NULL) */
+int ddpm_colsum(const ddpm_tensor* dy, int dtype, float* out_nc, float* dbias, void* stream);
+
+/* ---------------- convolution / linear as implicit GEMM ----------------------------------- */
+/* nn.Conv2d 3x3 s1/s2 p1, 1x1 (unet_backbone.py:22,32,35,51,60,97,100; attention.py:53-54) and
+ * nn.Linear as a 1x1 conv on H=W=1 (attention.py:30,32; unet_backbone.py:27). */
+#define DDPM_CONV_NORMAL 0
+#define DDPM_CONV_TRANSPOSED 1 /* gather for the data-gradient of a strided conv */
+#define DDPM_EPI_ACCUM 1       /* out += result (in place; gradient fan-in, residual) */
+#define DDPM_EPI_DSILU 2       /* result *= silu'(z[n,c])  (time path backward) */
+typedef struct {
+    ddpm_tensor in;        /* activations (or dY for dgrad) */
+    ddpm_tensor out;       /* result view (may be a channel slice of a wider buffer) */
+    const void* w;         /* packed weights [Cout][KH*KW][Cin] in `dtype` (see ddpm_pack_weights) */
+    const float* bias;     /* fp32 [Cout] or NULL */
+    const float* tbias;    /* per-image bias fp32 [N][tbias_pitch] or NULL (time_proj output; the time path is fp32) */
+    int32_t tbias_pitch;
+    ddpm_tensor res;       /* residual added in the epilogue; res.ptr == NULL for none */
+    ddpm_tensor z;         /* pre-activation for DDPM_EPI_DSILU; z.ptr == NULL for none */
+    int32_t KH, KW, stride, pad;
+    int32_t mode;          /* DDPM_CONV_NORMAL / DDPM_CONV_TRANSPOSED */
+    int32_t a_silu;        /* apply SiLU to the input operand on load (time path) */
+    int32_t epi;           /* DDPM_EPI_* flags */
+    int32_t dtype;
+    int32_t prefer_tc;     /* 1: use the tcgen05 kernel when the shape qualifies (bf16 only) */
+} ddpm_conv_args;
+int ddpm_conv(const ddpm_conv_args* a, void* stream);
+
+typedef struct {
+    ddpm_tensor act;   /* forward input operand of the conv */
+    ddpm_tensor dy;    /* gradient of the conv output */
+    float* dw;         /* fp32 OIHW [Cout][Cin][KH][KW], accumulated */
+    int32_t KH, KW, stride, pad;
+    int32_t a_silu;
+    int32_t dtype;
+    int32_t prefer_tc;
+} ddpm_wgrad_args;
+int ddpm_conv_wgrad(const ddpm_wgrad_args* a, void* stream);
+
+/* fp32 OIHW -> [Cout][KH*KW][Cin] (fwd) and flipped/transposed [Cin][KH*KW][Cout] (dgrad). */
+int ddpm_pack_weights(const float* w, int Cout, int Cin, int KH, int KW, void* w_fwd, void* w_dgrad,
+                      int dtype, void* stream);
+
+/* ---------------- attention: attention.py:56-74 -------------------------------------------- */
+/* qkv: NHWC with channel = s*heads*d + head*d + i (s in q,k,v) -- the layout conv `qkv` emits, so
+ * the four permute+contiguous copies (:63-65,72) disappear.  lse: fp32 [N][heads][H*W]. */
+int ddpm_attn_fwd(const ddpm_tensor* qkv, const ddpm_tensor* out, int heads, int d, float* lse,
+                  int dtype, void* stream);
+/* scratch: fp32 [N][heads][HW][HW] * 2 (P and dS) */
+int ddpm_attn_bwd(const ddpm_tensor* qkv, const ddpm_tensor* out, const ddpm_tensor* dout,
+                  const float* lse, const ddpm_tensor* dqkv, int heads, int d, float* scratch,
+                  int dtype, void* stream);
+
+/* ---------------- optimiser-side parameter pass -------------------------------------------- */
+/* train_one_epoch.py:94-115 + ema.py:15-23 over flat fp32 arenas.
+ * stats: fp32 [4] = {sum g^2 (of the still-scaled grads), found_inf flag, -, -}; zeroed by reduce. */
+int ddpm_param_reduce(const float* grad, int64_t n, float* stats, void* stream);
+typedef struct {
+    float lr, beta1, beta2, eps, weight_decay;
+    float max_norm;     /* <= 0: no clipping */
+    float ema_decay;    /* used when ema != NULL */
+    int32_t adamw;      /* 1: decoupled decay (AdamW); 0: L2 into the gradient (Adam) */
+} ddpm_adam_hyper;
+/* step: device fp32 [1], incremented when no inf was found (AdamW `state["step"]`).
+ * scale: the GradScaler's device `_scale` fp32 [1], or NULL for 1.0.
+ * One pass: g*=1/scale, clip by global norm, Adam(W) update, EMA lerp.  When found_inf, p/m/v are
+ * left untouched (GradScaler.step skip) but the EMA still moves (ema.update is unconditional). */
+int ddpm_param_update(float* p, const float* g, float* m, float* v, float* ema, int64_t n,
+                      const float* stats, float* step, const float* scale, const ddpm_adam_hyper* h,
+                      void* stream);
+/* GradScaler.update() on its own tensors: scale *= backoff on inf, *= growth after `interval`
+ * clean steps (tracker: int32 [1]). */
+int ddpm_scaler_update(float* scale, int32_t* tracker, const float* stats, float growth, float backoff,
+                       int interval, void* stream);
+/* For optimisers other than Adam(W): g *= clip/scale in place (g = 0 when inf was found). */
+int ddpm_grad_unscale_clip(float* g, int64_t n, const float* stats, const float* scale, float max_norm,
+                           void* stream);
+/* EMA only (any optimiser): shadow = d*shadow + (1-d)*p */
+int ddpm_ema_update(float* shadow, const float* p, int64_t n, float decay, void* stream);
+/* rng[1] += 1 (dropout stream position), graph-capturable */
+int ddpm_rng_advance(uint64_t* rng, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DDPM_B200_H */
