@@ -1,0 +1,281 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the DDPM/DDIM hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload train|ddim]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+           --master-port P bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): CelebA64 low-GPU UNetDenoiser (12.68 M params), T=1000 linear
+betas, bf16 autocast + GradScaler + AdamW(lr 2e-4) + EMA(0.9995) + grad-clip 1.0, batch 128 per GPU,
+synthetic 64x64 images, data-parallel over N GPUs (weak scaling).  One "step" = one optimiser step.
+
+  value    : images/s, whole job, batch already resident in HBM when the timed region starts
+  e2e      : same metric through the public API (`train_one_epoch`, one call per step) with the batch
+             in pinned HOST memory: H2D copy of the images and D2H read of the loss inside the timing
+  roofline : the dominant kernel (implicit-GEMM convolution) timed alone with CUDA events on the
+             launching stream, algorithmic FLOPs / time vs the measured bf16 peak
+  cpu_baseline / --impl reference : the oracle port of the reference (CPU, fp32, all host threads)
+             on a bounded sample (B=8, the reference's own CPU-runnable configs[0] shapes)
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+LOW_GPU = dict(base_channels=96, channel_mults=(1, 2, 2, 2), num_res_blocks=1, attn_resolutions={8},
+               num_heads=2, head_dim=32, dropout=0.1)
+TRAIN_GF_PER_IMG = 47.94      # SURVEY.md §8d (fprop+dgrad+wgrad, measured on the reference with hooks)
+FWD_GF_PER_IMG = 15.98
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sus=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sus=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop = index, [], threading.Event()
+        self.th = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.th.join(2)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = max([int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()] or [0])
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_train_imgs_per_s(steps, warmup, batch=8):
+    """One optimiser step of the reference algorithm (oracle port, fp32, dropout off) at B=8, 64px."""
+    from oracle import ddpm_oracle as O
+    torch.manual_seed(0)
+    from ddpm_diffusion_model_b200.model.unet_backbone import build_unet_64x64   # parameter init only (CPU tensors)
+    sd = {k: v.detach().clone() for k, v in build_unet_64x64(**LOW_GPU).state_dict().items()}
+    spec = O.UNetSpec(in_channels=3, time_embed_dim=512, img_resolution=64, **dict(LOW_GPU, dropout=0.0))
+    tb = O.make_tables()
+    torch.manual_seed(7)
+    x0 = torch.empty(batch, 3, 64, 64).uniform_(-1, 1)
+    opt, ema = {}, {k: v.clone() for k, v in sd.items()}
+    times = []
+    for i in range(warmup + steps):
+        t = torch.randint(1, 1000, (batch,))
+        noise = torch.randn_like(x0)
+        t0 = time.perf_counter()
+        _, _, sd, opt, ema = O.train_step(sd, spec, tb, x0, t, noise, opt, ema, lr=2e-4, step=i + 1, grad_clip=1.0, ema_decay=0.9995)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    dt = sum(times) / len(times)
+    return batch / dt, dt, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = min(args.steps, 4)
+    warm = min(args.warmup, 1) if args.warmup else 0
+    ips, dt, cores = cpu_train_imgs_per_s(steps, max(1, warm))
+    line = {
+        "impl": "reference", "metric": "train_img_per_s", "value": ips, "unit": "img/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": max(1, warm), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "CelebA64 low-GPU UNet train step (AdamW+EMA+clip), oracle port of the reference on host CPU",
+                   "batch": 8, "img": 64},
+        "cpu_baseline": {"value": ips, "unit": "img/s", "cores": cores, "kind": "port",
+                         "sample": f"{steps} optimiser steps at B=8, 64x64, fp32, dropout off"},
+        "e2e": {"value": ips, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def conv_roofline(device, batch, reps=5):
+    """Time the implicit-GEMM convolution kernel alone (fprop shapes of the low-GPU UNet at the bench
+    batch), CUDA events on the launching stream.  Returns (flops per pass, seconds per pass, detail)."""
+    from ddpm_diffusion_model_b200 import _lib, engine
+    E = engine.Exec(device, _lib.BF16, False, False)
+    # (Cin, Cout, H, count) -- SURVEY.md Appendix A.1, 3x3 s1 rows that make up 90 % of the FLOPs
+    shapes = [(96, 96, 64, 5), (192, 192, 32, 5), (192, 192, 64, 1), (288, 96, 64, 1), (384, 192, 32, 1),
+              (192, 192, 16, 6), (192, 192, 8, 9), (96, 192, 32, 1), (384, 192, 16, 1)]
+    tot_f, tot_t, detail = 0.0, 0.0, []
+    for ci, co, hw, cnt in shapes:
+        w = torch.nn.Parameter(torch.randn(co, ci, 3, 3, device=device) * 0.02)
+        wf, _ = E.wcache.get(E, w, _lib.BF16, False)
+        x = E.act(batch, hw, hw, ci)
+        x.interior().normal_()
+        y = E.act(batch, hw, hw, co)
+        engine.conv(E, x, wf, y, 3, 1, 1)
+        torch.cuda.synchronize(device)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(reps):
+            engine.conv(E, x, wf, y, 3, 1, 1)
+        e.record()
+        torch.cuda.synchronize(device)
+        dt = s.elapsed_time(e) / 1e3 / reps
+        fl = 2.0 * batch * hw * hw * co * ci * 9
+        detail.append({"shape": f"{ci}->{co}@{hw}", "tflops": fl / dt / 1e12, "us": dt * 1e6})
+        tot_f += fl * cnt
+        tot_t += dt * cnt
+        del x, y
+    return tot_f, tot_t, detail
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from ddpm_diffusion_model_b200 import _lib
+    from ddpm_diffusion_model_b200.model.difussion_class import Diffusion
+    from ddpm_diffusion_model_b200.model.unet_backbone import build_unet_64x64
+    from ddpm_diffusion_model_b200.training_loops.ema import EMA
+    from ddpm_diffusion_model_b200.training_loops.grad_scaler import make_grad_scaler
+    from ddpm_diffusion_model_b200.training_loops.train_one_epoch import train_one_epoch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    torch.manual_seed(0)
+    model = build_unet_64x64(**LOW_GPU).to(dev)
+    diff = Diffusion(T=1000, schedule="linear", beta_min=1e-4, beta_max=2e-2, img_size=64).to(dev)
+    opt = torch.optim.AdamW(model.parameters(), lr=2e-4, betas=(0.9, 0.999), weight_decay=0.0)
+    ema = EMA(model, decay=0.9995)
+    scaler = make_grad_scaler("cuda", True)
+    torch.manual_seed(7 + rank)
+    x_host = torch.empty(B, 3, 64, 64).uniform_(-1, 1).pin_memory()
+    y_host = torch.zeros(B)
+    x_dev = x_host.to(dev)
+
+    def step_resident():
+        return train_one_epoch(model, diff, [(x_dev, y_host)], opt, scaler=scaler, ema=ema, device=f"cuda:{local}", grad_clip=1.0)
+
+    def step_e2e():
+        return train_one_epoch(model, diff, [(x_host, y_host)], opt, scaler=scaler, ema=ema, device=f"cuda:{local}", grad_clip=1.0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, K):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        _lib.launch_count(reset=True)
+        s.record()
+        last = None
+        for _ in range(K):
+            last = fn()
+        e.record()
+        barrier()
+        ms = s.elapsed_time(e)
+        n_launch = _lib.launch_count(reset=True)
+        if world > 1:
+            tt = torch.tensor([ms], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt)
+        return ms / 1e3, n_launch, last
+
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    with ClockSampler(local) as clk:
+        sec, launches, last = timed(step_resident, args.steps)
+    for _ in range(2):
+        step_e2e()
+    sec_e2e, _, last_e2e = timed(step_e2e, args.steps)
+    value = world * B * args.steps / sec
+    e2e = world * B * args.steps / sec_e2e
+
+    roof = cpu = None
+    if rank == 0:
+        pk = peaks()
+        fl, tt, detail = conv_roofline(dev, B)
+        ach = fl / tt / 1e12
+        roof = {"bound": "tensor", "achieved": ach, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": ach / pk["tf_burst"],
+                "traffic": None, "kernel": "implicit-GEMM conv fprop (3x3 s1 layers of the low-GPU UNet, B=%d)" % B,
+                "peak_source": pk["src"] + " bf16 burst (kernel timed alone)", "per_shape": detail,
+                "step_tensor_frac": (TRAIN_GF_PER_IMG * 1e9 * world * B * args.steps / sec) / (world * pk["tf_sus"] * 1e12)}
+        if world == 1 and not args.no_cpu:
+            ips, dt, cores = cpu_train_imgs_per_s(2, 1)
+            cpu = {"value": ips, "unit": "img/s", "cores": cores, "kind": "port",
+                   "sample": "2 optimiser steps (after 1 warm-up) of the oracle port at B=8, 64x64, fp32"}
+    if rank == 0:
+        line = {
+            "metric": "train_img_per_s", "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "CelebA64 low-GPU UNet (12.68M) training step: bf16 autocast + GradScaler + AdamW + EMA + clip",
+                       "batch_per_gpu": B, "global_batch": B * world, "img": 64, "T": 1000, "parallelism": f"dp{world}",
+                       "l2": "working set per step (~3 GB of activations) exceeds the 126 MB L2; no explicit flush"},
+            "e2e": {"value": e2e, "unit": "img/s", "h2d_bytes_per_step": B * 3 * 64 * 64 * 4, "d2h_bytes_per_step": 4,
+                    "ms_per_step": sec_e2e / args.steps * 1e3},
+            "gpu_launches": launches, "clocks": clk.summary(), "roofline": roof, "cpu_baseline": cpu,
+            "loss": last[0] if last else None,
+            "train_tflops_per_gpu": TRAIN_GF_PER_IMG * 1e9 * B * args.steps / sec / 1e12,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=128)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

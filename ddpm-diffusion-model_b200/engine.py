@@ -16,6 +16,7 @@ in reverse order.  Nothing here touches the oracle and nothing falls back to ATe
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -138,9 +139,14 @@ class WeightCache:
     def get(self, E: "Exec", w: torch.Tensor, dt: int, need_dgrad: bool):
         key = (id(w), dt)
         ent = self.entries.get(key)
+        if ent is not None and ent[4]() is not w:          # id() reused by a new parameter object
+            ent = None
         stamp = (w._version, self.epoch, w.data_ptr())
         if ent is not None and ent[0] == stamp and (ent[2] is not None or not need_dgrad):
             return ent[1], ent[2]
+        if ent is None and len(self.entries) > 64:
+            for k in [k for k, e in self.entries.items() if e[4]() is None]:
+                del self.entries[k]
         co, ci = w.shape[0], w.shape[1]
         kh, kw = (w.shape[2], w.shape[3]) if w.dim() == 4 else (1, 1)
         tdt = _TORCH[dt]
@@ -153,7 +159,7 @@ class WeightCache:
             wd = wd.contiguous()
         _lib.call("ddpm_pack_weights", wd.data_ptr(), co, ci, kh, kw, fwd.data_ptr(),
                   dg.data_ptr() if dg is not None else None, dt, E.stream)
-        self.entries[key] = (stamp, fwd, dg, wd)
+        self.entries[key] = (stamp, fwd, dg, wd, weakref.ref(w))
         return fwd, dg
 
 

@@ -342,7 +342,7 @@ def _build(cfg):
     return UNetDenoiser(**kw)
 
 
-def _unet_case(golden, name, autocast, tol_out, tol_grad):
+def _unet_case(golden, name, autocast, tol_out, tol_grad, floor=1e-3):
     from ddpm_diffusion_model_b200.model.difussion_class import Diffusion
     g = golden(name)
     sd = g["state_dict"]
@@ -369,7 +369,7 @@ def _unet_case(golden, name, autocast, tol_out, tol_grad):
         if k not in g["grads"]:
             continue
         ref = g["grads"][k]
-        e = float((p.grad.detach().double().cpu() - ref.double()).norm()) / max(float(ref.norm()), 1e-3 * gmax)
+        e = float((p.grad.detach().double().cpu() - ref.double()).norm()) / max(float(ref.norm()), floor * gmax)
         if e > worst:
             worst, worst_k = e, k
     assert worst < tol_grad, (worst_k, worst)
@@ -390,7 +390,9 @@ def test_unet_fp32_other_resolution(golden):
 def test_unet_bf16_attn(golden):
     # bf16 tolerance 2e-2 on the forward (north_star); gradients of a random-init net accumulate
     # bf16 rounding through ~20 layers, measured against the fp32 reference: 6e-2 of the tensor norm
-    _unet_case(golden, "unet_tiny_attn.pt", True, 2e-2, 6e-2)
+    # (tensors whose true gradient is ~0 -- biases in front of a GroupNorm -- are measured against
+    # a floor of 1 % of the largest gradient norm)
+    _unet_case(golden, "unet_tiny_attn.pt", True, 2e-2, 6e-2, floor=1e-2)
 
 
 def test_standalone_modules_vs_aten():
