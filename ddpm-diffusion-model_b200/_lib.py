@@ -84,6 +84,7 @@ SIGNATURES = {
     "ddpm_ema_update": [_vp, _vp, _i64, _f, _vp],
     "ddpm_rng_advance": [_vp, _vp],
     "ddpm_set_force_simt": [_i],
+    "ddpm_set_tc_mode": [_i, _i],
 }
 
 

@@ -1,7 +1,416 @@
-// tcgen05 / TMEM implicit-GEMM convolution (bf16).  Placeholder until the tensor-core kernels land:
-// reports "unsupported" so ddpm_conv dispatches every shape to conv_simt.cu.
+// tcgen05 / TMEM implicit-GEMM convolution for sm_100a (bf16 in, fp32 accumulate in tensor memory).
+//
+// "Shift-GEMM" over the padded NHWC layout.  Activations carry a zero halo, so with
+// Q = (n*Hp + yp)*Wp + xp the padded-linear pixel index, a 3x3/s1/p1 convolution is
+//     out[Q][co] = sum_{ky,kx} sum_ci  A[Q + (ky-1)*Wp + (kx-1)][ci] * W[co][ky][kx][ci]
+// for every interior Q: each filter tap is a constant ROW SHIFT of the same [pixels x channels]
+// matrix.  A CTA therefore stages one halo'd patch of 128*MT + 2*Wp + 2 pixel rows per 16-channel
+// K-chunk ONCE (TMA, zero-filled outside the tensor) and issues all nine taps as tcgen05.mma
+// instructions whose shared-memory descriptors differ only in their start address -- the 9x im2col
+// re-read of the activation never happens (neither from HBM nor from L2).  Outputs computed at halo
+// positions are discarded by the epilogue, which keeps the output halo zero.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA
+// issuer, warps 2..5 = epilogue (tcgen05.ld -> +bias +time-bias +residual -> bf16 -> global).
+// Two mbarrier rings: A patches (one per K-chunk) and B weight tiles (TPB taps x NT x 16ch).
+// Accumulators: MT tiles of 128 x NT fp32 in TMEM (MT*NT <= 256 columns so two CTAs share an SM and
+// one CTA's epilogue overlaps the other's main loop).
+//
+// Replaces cuDNN behind nn.Conv2d 3x3 s1 / 1x1 (unet_backbone.py:22,32,35,60; attention.py:53-54)
+// for fprop and, with flipped/transposed weights, dgrad.
 #include "common.cuh"
-int conv_tc_supported(const ddpm_conv_args*) { return 0; }
-int conv_tc_launch(const ddpm_conv_args*, cudaStream_t) { return DDPM_E_ARG; }
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#define TC_THREADS 192
+#define KC 16                 // channels per K-chunk (one UMMA K step for bf16)
+
+static int g_tc_mode = 1;     // 0: SWIZZLE_NONE ("interleave") operand layout, 1: SWIZZLE_32B (default)
+static int g_tc_baseoff = 0;  // measured on B200: the swizzle is a pure function of the smem address, so row-shifted
+                              // descriptors need base_offset = 0 (setting it from the address gives wrong results)
+extern "C" int ddpm_set_tc_mode(int mode, int baseoff) { g_tc_mode = mode; g_tc_baseoff = baseoff; return 0; }
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout, uint32_t base_off) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
+    d |= (uint64_t)(base_off & 7) << 49;
+    d |= (uint64_t)(layout & 7) << 61;
+    return d;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------------
+struct TcParams {
+    TV out, res;
+    const float* bias; const float* tbias; int tbias_pitch;
+    int Cin, Cout, NT;          // NT: output-channel tile (UMMA N), multiple of 16, <= 256
+    int taps, tpb;              // 9 (3x3) or 1; taps per B stage (3 or 1)
+    int Hp, Wp, H, W, Qtot;     // padded geometry shared by input and output
+    int P, seg;                 // patch rows per A stage = nseg * seg (seg = TMA box height, multiple of 8)
+    int SA, SB;                 // ring depths
+    int a_stage_bytes, b_stage_bytes;
+    int tmem_cols;              // power of two >= MT*NT
+    int has_res, accum;
+    int baseoff;
+};
+
+template <int MT, bool SW32>
+__global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                              const __grid_constant__ CUtensorMap tmB, TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* a_ring = smem;
+    uint8_t* b_ring = a_ring + (size_t)p.SA * p.a_stage_bytes;
+    uint64_t* bars = (uint64_t*)(b_ring + (size_t)p.SB * p.b_stage_bytes);
+    uint64_t* a_full = bars;            uint64_t* a_empty = a_full + p.SA;
+    uint64_t* b_full = a_empty + p.SA;  uint64_t* b_empty = b_full + p.SB;
+    uint64_t* acc_full = b_empty + p.SB;
+    uint32_t* tmem_slot = (uint32_t*)(acc_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int Q0 = blockIdx.x * (128 * MT);
+    const int n0 = blockIdx.y * p.NT;
+    const int KCH = p.Cin / KC;                         // K chunks
+    const int BG = p.taps / p.tpb;                      // B stages per K chunk
+    const int row_bytes = SW32 ? 32 : 16;               // bytes between consecutive pixel rows in smem
+    const int halo_rows = (p.taps == 9) ? p.Wp + 1 : 0; // rows in front of the tile inside the patch
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < p.SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < p.SB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================================================================== TMA producer
+        if (lane == 0) {
+            int sb = 0; uint32_t pb = 0;
+            for (int kc = 0; kc < KCH; ++kc) {
+                const int sa = kc % p.SA; const uint32_t pa = (kc / p.SA) & 1;
+                mbar_wait(&a_empty[sa], pa ^ 1);
+                uint8_t* adst = a_ring + (size_t)sa * p.a_stage_bytes;
+                mbar_expect_tx(&a_full[sa], (uint32_t)(p.P * 32));
+                const int row0 = Q0 - halo_rows;
+                for (int r = 0; r < p.P; r += p.seg) {          // one TMA box of `seg` rows per op
+                    if (SW32) {
+                        tma_load_2d(adst + (size_t)r * 32, &tmA, &a_full[sa], kc * KC, row0 + r);
+                    } else {
+                        tma_load_3d(adst + (size_t)r * 16, &tmA, &a_full[sa], 0, row0 + r, kc * 2);
+                        tma_load_3d(adst + (size_t)p.P * 16 + (size_t)r * 16, &tmA, &a_full[sa], 0, row0 + r, kc * 2 + 1);
+                    }
+                }
+                for (int g = 0; g < BG; ++g) {
+                    mbar_wait(&b_empty[sb], pb ^ 1);
+                    uint8_t* bdst = b_ring + (size_t)sb * p.b_stage_bytes;
+                    mbar_expect_tx(&b_full[sb], (uint32_t)(p.tpb * p.NT * 32));
+                    for (int t = 0; t < p.tpb; ++t) {
+                        const int tap = g * p.tpb + t;
+                        if (SW32) tma_load_3d(bdst + (size_t)t * p.NT * 32, &tmB, &b_full[sb], kc * KC, tap, n0);
+                        else tma_load_4d(bdst + (size_t)t * p.NT * 32, &tmB, &b_full[sb], 0, n0, kc * 2, tap);
+                    }
+                    if (++sb == p.SB) { sb = 0; pb ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================================== MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t layout = SW32 ? 6u : 0u;
+            const uint32_t a_lbo = SW32 ? 16u : (uint32_t)p.P * 16u;
+            const uint32_t b_lbo = SW32 ? 16u : (uint32_t)p.NT * 16u;
+            const uint32_t sbo = SW32 ? 256u : 128u;
+            int sb = 0; uint32_t pb = 0;
+            for (int kc = 0; kc < KCH; ++kc) {
+                const int sa = kc % p.SA; const uint32_t pa = (kc / p.SA) & 1;
+                mbar_wait(&a_full[sa], pa);
+                tc_fence_after();
+                const uint32_t a_base = smem_u32(a_ring + (size_t)sa * p.a_stage_bytes);
+                for (int g = 0; g < BG; ++g) {
+                    mbar_wait(&b_full[sb], pb);
+                    tc_fence_after();
+                    const uint32_t b_base = smem_u32(b_ring + (size_t)sb * p.b_stage_bytes);
+                    for (int t = 0; t < p.tpb; ++t) {
+                        const int tap = g * p.tpb + t;
+                        const int shift = (p.taps == 9) ? (tap / 3) * p.Wp + (tap % 3) : 0;
+                        const uint32_t baddr = b_base + (uint32_t)(t * p.NT * 32);
+                        const uint64_t bdesc = make_desc(baddr, b_lbo, sbo, layout, 0);
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt) {
+                            const uint32_t aaddr = a_base + (uint32_t)((mt * 128 + shift) * row_bytes);
+                            const uint32_t boff = (SW32 && p.baseoff) ? ((aaddr >> 7) & 7u) : 0u;
+                            const uint64_t adesc = make_desc(aaddr, a_lbo, sbo, layout, boff);
+                            umma_bf16(tmem_base + (uint32_t)(mt * p.NT), adesc, bdesc, idesc, (kc | tap) != 0 ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(&b_empty[sb]);
+                    if (++sb == p.SB) { sb = 0; pb ^= 1; }
+                }
+                umma_commit(&a_empty[sa]);
+            }
+            umma_commit(acc_full);
+        }
+    } else {
+        // ===================================================================== epilogue
+        const int qd = warp & 3;                         // TMEM lane quarter this warp may read
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        const int HpWp = p.Hp * p.Wp;
+#pragma unroll 1
+        for (int mt = 0; mt < MT; ++mt) {
+            const int Q = Q0 + mt * 128 + qd * 32 + lane;
+            bool valid = Q < p.Qtot;
+            int n = 0, y = 0, x = 0;
+            if (valid) {
+                n = Q / HpWp; int r = Q - n * HpWp; int yp = r / p.Wp; int xp = r - yp * p.Wp;
+                y = yp - 1; x = xp - 1;
+                valid = y >= 0 && y < p.H && x >= 0 && x < p.W;
+            }
+            bf16* orow = valid ? p.out.at<bf16>(n, y, x, n0) : nullptr;
+            const bf16* rrow = (valid && p.has_res) ? p.res.at<bf16>(n, y, x, n0) : nullptr;
+            const float* tb = (valid && p.tbias) ? p.tbias + (size_t)n * p.tbias_pitch + n0 : nullptr;
+#pragma unroll 1
+            for (int c0 = 0; c0 < p.NT; c0 += 16) {
+                uint32_t r[16];
+                tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(mt * p.NT + c0), r);
+                tmem_ld_wait();
+                if (valid && n0 + c0 < p.Cout) {
+                    float v[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+                    if (p.bias) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + n0 + c0 + i);
+                    }
+                    if (tb) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] += __ldg(tb + c0 + i);
+                    }
+                    if (rrow) {
+                        uint4 a = *reinterpret_cast<const uint4*>(rrow + c0), b = *reinterpret_cast<const uint4*>(rrow + c0 + 8);
+                        const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
+                        const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&b);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            float2 fa = __bfloat1622float2(ha[i]), fb = __bfloat1622float2(hb[i]);
+                            v[2 * i] += fa.x; v[2 * i + 1] += fa.y; v[8 + 2 * i] += fb.x; v[8 + 2 * i + 1] += fb.y;
+                        }
+                    }
+                    if (p.accum) {
+                        uint4 a = *reinterpret_cast<const uint4*>(orow + c0), b = *reinterpret_cast<const uint4*>(orow + c0 + 8);
+                        const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
+                        const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&b);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            float2 fa = __bfloat1622float2(ha[i]), fb = __bfloat1622float2(hb[i]);
+                            v[2 * i] += fa.x; v[2 * i + 1] += fa.y; v[8 + 2 * i] += fb.x; v[8 + 2 * i + 1] += fb.y;
+                        }
+                    }
+                    uint4 o0, o1;
+                    __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&o0);
+                    __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&o1);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        h0[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                        h1[i] = __floats2bfloat162_rn(v[8 + 2 * i], v[8 + 2 * i + 1]);
+                    }
+                    *reinterpret_cast<uint4*>(orow + c0) = o0;
+                    *reinterpret_cast<uint4*>(orow + c0 + 8) = o1;
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+static int get_encode() {
+    if (g_encode) return 0;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) return 801;   // cudaErrorNotSupported
+    g_encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+    return 0;
+}
+
+static int encode(CUtensorMap* m, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box, CUtensorMapSwizzle sw) {
+    cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];
+    for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i < rank - 1; ++i) gs[i] = strides_bytes[i];
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, gd, gs, bx, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : 1;   // cudaErrorInvalidValue
+}
+
+static int pick_nt(int Cout) {
+    if (Cout <= 256) return Cout;
+    for (int nt = 256; nt >= 64; nt -= 16) if (Cout % nt == 0) return nt;
+    return 0;
+}
+
+int conv_tc_supported(const ddpm_conv_args* a) {
+    if (a->dtype != DDPM_BF16 || a->mode != DDPM_CONV_NORMAL || a->stride != 1 || a->a_silu || a->z.ptr) return 0;
+    if (!((a->KH == 3 && a->KW == 3 && a->pad == 1) || (a->KH == 1 && a->KW == 1 && a->pad == 0))) return 0;
+    const ddpm_tensor &in = a->in, &out = a->out;
+    if (in.halo != 1 || out.halo != 1 || in.H != out.H || in.W != out.W || in.N != out.N) return 0;
+    if (in.C % 16 || out.C % 16 || in.pitch % 8 || out.pitch % 8) return 0;
+    if (((uintptr_t)in.ptr & 15) || ((uintptr_t)out.ptr & 15) || ((uintptr_t)a->w & 15)) return 0;
+    if (a->res.ptr && (a->res.halo != 1 || a->res.pitch % 8 || ((uintptr_t)a->res.ptr & 15))) return 0;
+    if (pick_nt(out.C) == 0) return 0;
+    if (in.W + 2 > 300) return 0;         // patch would not fit the A ring (large images: later round)
+    return 1;
+}
+
+template <int MT, bool SW32>
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+    static size_t configured = 0;
+    if (smem > configured) {
+        CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<MT, SW32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    conv_tc_kernel<MT, SW32><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, p);
+    LAUNCH_OK();
+    return 0;
+}
+
+int conv_tc_launch(const ddpm_conv_args* a, cudaStream_t st) {
+    int rc = get_encode(); if (rc) return rc;
+    const bool sw32 = g_tc_mode == 1;
+    TcParams p;
+    p.out = TV(a->out);
+    p.has_res = a->res.ptr != nullptr; p.res = p.has_res ? TV(a->res) : TV(a->out);
+    p.bias = a->bias; p.tbias = a->tbias; p.tbias_pitch = a->tbias_pitch;
+    p.Cin = a->in.C; p.Cout = a->out.C; p.NT = pick_nt(p.Cout);
+    p.taps = a->KH * a->KW; p.tpb = p.taps == 9 ? 3 : 1;
+    p.Hp = a->in.H + 2; p.Wp = a->in.W + 2; p.H = a->in.H; p.W = a->in.W;
+    p.Qtot = a->in.N * p.Hp * p.Wp;
+    p.accum = (a->epi & DDPM_EPI_ACCUM) ? 1 : 0;
+    p.baseoff = g_tc_baseoff;
+    int MT = 256 / p.NT; if (MT >= 2) MT = 2; if (MT < 1) MT = 1;
+    int halo_rows = p.taps == 9 ? p.Wp + 1 : 0;
+    {
+        int need = 128 * MT + 2 * halo_rows;
+        int nseg = (need + 255) / 256;
+        p.seg = (((need + nseg - 1) / nseg) + 7) & ~7;
+        p.P = p.seg * nseg;
+    }
+    p.a_stage_bytes = (p.P * 32 + 1023) & ~1023;
+    p.b_stage_bytes = (p.tpb * p.NT * 32 + 1023) & ~1023;
+    p.tmem_cols = 32; while (p.tmem_cols < MT * p.NT) p.tmem_cols <<= 1;
+    // ring depths inside ~110 KB so two CTAs are co-resident per SM
+    const int budget = 108 * 1024;
+    p.SA = 3; p.SB = 4;
+    while (p.SA > 2 && p.SA * p.a_stage_bytes + p.SB * p.b_stage_bytes > budget) --p.SA;
+    while (p.SB > 2 && p.SA * p.a_stage_bytes + p.SB * p.b_stage_bytes > budget) --p.SB;
+    size_t smem = (size_t)p.SA * p.a_stage_bytes + (size_t)p.SB * p.b_stage_bytes + 8 * (2 * p.SA + 2 * p.SB + 1) + 16 + 1024;
+    if (smem > 227 * 1024) return DDPM_E_ARG;
+
+    CUtensorMap tmA, tmB;
+    const uint64_t rows = (uint64_t)p.Qtot;
+    const uint32_t abox_rows = (uint32_t)p.seg;
+    if (sw32) {
+        uint64_t da[2] = {(uint64_t)p.Cin, rows}; uint64_t sa[1] = {(uint64_t)a->in.pitch * 2};
+        uint32_t ba[2] = {KC, abox_rows};
+        if (encode(&tmA, a->in.ptr, 2, da, sa, ba, CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
+        uint64_t db[3] = {(uint64_t)p.Cin, (uint64_t)p.taps, (uint64_t)p.Cout};
+        uint64_t sb[2] = {(uint64_t)p.Cin * 2, (uint64_t)p.taps * p.Cin * 2};
+        uint32_t bb[3] = {KC, 1, (uint32_t)p.NT};
+        if (encode(&tmB, (void*)a->w, 3, db, sb, bb, CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
+    } else {
+        uint64_t da[3] = {8, rows, (uint64_t)p.Cin / 8}; uint64_t sa[2] = {(uint64_t)a->in.pitch * 2, 16};
+        uint32_t ba[3] = {8, abox_rows, 1};
+        if (encode(&tmA, a->in.ptr, 3, da, sa, ba, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
+        uint64_t db[4] = {8, (uint64_t)p.Cout, (uint64_t)p.Cin / 8, (uint64_t)p.taps};
+        uint64_t sb[3] = {(uint64_t)p.taps * p.Cin * 2, 16, (uint64_t)p.Cin * 2};
+        uint32_t bb[4] = {8, (uint32_t)p.NT, 2, 1};
+        if (encode(&tmB, (void*)a->w, 4, db, sb, bb, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
+    }
+    dim3 grid(ceil_div(p.Qtot, 128 * MT), p.Cout / p.NT);
+    if (MT == 2) return sw32 ? launch<2, true>(tmA, tmB, p, grid, smem, st) : launch<2, false>(tmA, tmB, p, grid, smem, st);
+    return sw32 ? launch<1, true>(tmA, tmB, p, grid, smem, st) : launch<1, false>(tmA, tmB, p, grid, smem, st);
+}
+
 int wgrad_tc_supported(const ddpm_wgrad_args*) { return 0; }
 int wgrad_tc_launch(const ddpm_wgrad_args*, cudaStream_t) { return DDPM_E_ARG; }

@@ -135,6 +135,10 @@ typedef struct {
     int32_t prefer_tc;     /* 1: use the tcgen05 kernel when the shape qualifies (bf16 only) */
 } ddpm_conv_args;
 int ddpm_conv(const ddpm_conv_args* a, void* stream);
+/* test / tuning hooks: force the CUDA-core kernels; choose the tcgen05 operand layout
+ * (0 = SWIZZLE_NONE, 1 = SWIZZLE_32B [+ descriptor base_offset]) */
+int ddpm_set_force_simt(int on);
+int ddpm_set_tc_mode(int mode, int base_offset);
 
 typedef struct {
     ddpm_tensor act;   /* forward input operand of the conv */
