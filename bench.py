@@ -220,6 +220,15 @@ def run_ours(args):
             ms = float(tt)
         return ms / 1e3, n_launch, last
 
+    if args.profile:                                  # short run for `ncu` launch lists
+        for _ in range(2):
+            step_resident()
+        torch.cuda.synchronize(dev)
+        torch.cuda.nvtx.range_push("timed_step")
+        step_resident()
+        torch.cuda.synchronize(dev)
+        torch.cuda.nvtx.range_pop()
+        return
     for _ in range(max(3, args.warmup)):
         step_resident()
     with ClockSampler(local) as clk:
@@ -270,6 +279,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=128)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--profile", action="store_true", help="2 warm-up steps + 1 step, no JSON (for ncu)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -28,14 +28,15 @@ class ConvArgs(C.Structure):
                 ("tbias", C.c_void_p), ("tbias_pitch", C.c_int32), ("res", Tensor), ("z", Tensor),
                 ("KH", C.c_int32), ("KW", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32),
                 ("mode", C.c_int32), ("a_silu", C.c_int32), ("epi", C.c_int32), ("dtype", C.c_int32),
-                ("prefer_tc", C.c_int32)]
+                ("prefer_tc", C.c_int32), ("bias_n", C.c_int32)]
 
 
 class WgradArgs(C.Structure):
     """struct ddpm_wgrad_args"""
     _fields_ = [("act", Tensor), ("dy", Tensor), ("dw", C.c_void_p), ("KH", C.c_int32),
                 ("KW", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32), ("a_silu", C.c_int32),
-                ("dtype", C.c_int32), ("prefer_tc", C.c_int32)]
+                ("dtype", C.c_int32), ("prefer_tc", C.c_int32), ("workspace", C.c_void_p),
+                ("workspace_bytes", C.c_int64), ("cin_valid", C.c_int32), ("cout_valid", C.c_int32)]
 
 
 class AdamHyper(C.Structure):
@@ -62,7 +63,7 @@ SIGNATURES = {
     "ddpm_p_sample_step": [_vp, _vp, _vp, _i, _vp, _vp, _vp, _f, _i, _vp, _i, _i64, _vp],
     "ddpm_ddim_step": [_vp, _vp, _vp, _i, _vp, _vp, _vp, _f, _vp, _f, _i, _vp, _i, _i64, _vp],
     "ddpm_to_image01": [_vp, _vp, _i64, _vp],
-    "ddpm_nchw_to_nhwc": [_vp, _i, _i64, _i64, _i64, _i64, _TP, _i, _vp],
+    "ddpm_nchw_to_nhwc": [_vp, _i, _i, _i64, _i64, _i64, _i64, _TP, _i, _vp],
     "ddpm_nhwc_to_nchw": [_TP, _i, _vp, _i, _i64, _i64, _i64, _i64, _vp],
     "ddpm_sinusoid": [_vp, _i, _i, _i, _vp, _i, _vp],
     "ddpm_gn_stats": [_TP, _i, _i, _vp, _vp],
@@ -70,11 +71,13 @@ SIGNATURES = {
     "ddpm_gn_bwd": [_TP, _i, _i, _vp, _vp, _vp, _f, _i, _f, _vp, _u32, _TP, _TP, _i, _vp, _vp, _vp, _vp],
     "ddpm_upsample2x": [_TP, _TP, _i, _vp],
     "ddpm_upsample2x_bwd": [_TP, _TP, _i, _i, _vp],
+    "ddpm_zero_upsample2x": [_TP, _TP, _i, _vp],
     "ddpm_add": [_TP, _TP, _TP, _i, _vp],
     "ddpm_colsum": [_TP, _i, _vp, _vp, _vp],
     "ddpm_conv": [C.POINTER(ConvArgs), _vp],
     "ddpm_conv_wgrad": [C.POINTER(WgradArgs), _vp],
-    "ddpm_pack_weights": [_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp],
+    "ddpm_wgrad_workspace_bytes": [C.POINTER(WgradArgs)],
+    "ddpm_pack_weights": [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp],
     "ddpm_attn_fwd": [_TP, _TP, _i, _i, _vp, _i, _vp],
     "ddpm_attn_bwd": [_TP, _TP, _TP, _vp, _TP, _i, _i, _vp, _i, _vp],
     "ddpm_param_reduce": [_vp, _i64, _vp, _vp],
@@ -96,7 +99,7 @@ def _load() -> C.CDLL:
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)        # AttributeError if the ABI symbol is missing
         fn.argtypes = argtypes
-        fn.restype = C.c_int64 if name == "ddpm_launch_count" else C.c_int
+        fn.restype = C.c_int64 if name in ("ddpm_launch_count", "ddpm_wgrad_workspace_bytes") else C.c_int
     return lib
 
 

@@ -38,6 +38,6 @@ extern "C" int ddpm_conv_wgrad(const ddpm_wgrad_args* a, void* stream) {
     if (a->dy.H != (a->act.H + 2 * a->pad - a->KH) / a->stride + 1) return DDPM_E_ARG;
     if (a->dy.W != (a->act.W + 2 * a->pad - a->KW) / a->stride + 1) return DDPM_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    if (a->prefer_tc && !g_force_simt && wgrad_tc_supported(a)) return wgrad_tc_launch(a, st);
+    if (a->prefer_tc && !g_force_simt && a->workspace && wgrad_tc_supported(a)) return wgrad_tc_launch(a, st);
     return wgrad_simt_launch(a, st);
 }

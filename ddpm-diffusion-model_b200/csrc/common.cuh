@@ -126,6 +126,31 @@ __device__ __forceinline__ uint4 philox4(uint32_t k0, uint32_t k1, uint4 c) {
     }
     return c;
 }
+// keep-bits for VEC consecutive elements starting at `e0` (e0 % VEC == 0 for VEC in {4, 8}): one
+// Philox call per 4 elements; bit i set = keep element e0+i.  Same function in forward and backward.
+template <int VEC>
+__device__ __forceinline__ uint32_t dropout_mask(const uint64_t* rng, uint32_t layer, uint64_t e0, float p) {
+    const uint64_t seed = rng[0], step = rng[1];
+    const uint32_t thr = (uint32_t)(p * 16777216.0f);            // keep iff (w >> 8) >= thr
+    uint32_t m = 0;
+    if (VEC == 1) {
+        uint4 r = philox4((uint32_t)seed, (uint32_t)(seed >> 32),
+                          make_uint4((uint32_t)(e0 >> 2), (uint32_t)(e0 >> 34), (uint32_t)step, layer));
+        uint32_t w = (e0 & 3) == 0 ? r.x : (e0 & 3) == 1 ? r.y : (e0 & 3) == 2 ? r.z : r.w;
+        return (w >> 8) >= thr ? 1u : 0u;
+    }
+#pragma unroll
+    for (int q = 0; q < VEC / 4; ++q) {
+        uint64_t e = (e0 >> 2) + q;
+        uint4 r = philox4((uint32_t)seed, (uint32_t)(seed >> 32),
+                          make_uint4((uint32_t)e, (uint32_t)(e >> 32), (uint32_t)step, layer));
+        m |= ((r.x >> 8) >= thr ? 1u : 0u) << (4 * q);
+        m |= ((r.y >> 8) >= thr ? 1u : 0u) << (4 * q + 1);
+        m |= ((r.z >> 8) >= thr ? 1u : 0u) << (4 * q + 2);
+        m |= ((r.w >> 8) >= thr ? 1u : 0u) << (4 * q + 3);
+    }
+    return m;
+}
 // keep-mask for element index `e` (one Philox call covers 4 consecutive elements)
 __device__ __forceinline__ bool dropout_keep(const uint64_t* rng, uint32_t layer, uint64_t e, float p) {
     uint64_t seed = rng[0], step = rng[1];

@@ -21,7 +21,7 @@ struct ConvP {
     TV in, out, res, z;
     const void* w; const float* bias; const float* tbias; int tbias_pitch;
     int KH, KW, stride, pad, mode, a_silu, epi;
-    int Cin, Cout, M, Kt, HoWo;
+    int Cin, Cout, M, Kt, HoWo, bias_n;
     int vecA, vecB, vecO, has_res, has_z;
 };
 
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(CT) conv_simt_kernel(ConvP p) {
             int co = co0 + j;
             float x = acc[i][j];
             if (co < p.Cout) {
-                if (p.bias) x += p.bias[co];
+                if (p.bias && co < p.bias_n) x += p.bias[co];
                 if (tb) x += tb[(int64_t)n * p.tbias_pitch + co];
                 if (p.has_res) x += ldf<T>(p.res.at<T>(n, oy, ox, co));
                 if (p.has_z) x *= dsilu_f(ldf<T>(p.z.at<T>(n, oy, ox, co)));
@@ -195,7 +195,7 @@ int conv_simt_launch(const ddpm_conv_args* a, cudaStream_t st) {
     p.w = a->w; p.bias = a->bias; p.tbias = a->tbias; p.tbias_pitch = a->tbias_pitch;
     p.KH = a->KH; p.KW = a->KW; p.stride = a->stride; p.pad = a->pad; p.mode = a->mode;
     p.a_silu = a->a_silu; p.epi = a->epi;
-    p.Cin = a->in.C; p.Cout = a->out.C;
+    p.Cin = a->in.C; p.Cout = a->out.C; p.bias_n = a->bias_n > 0 ? a->bias_n : a->out.C;
     p.HoWo = a->out.H * a->out.W; p.M = a->out.N * p.HoWo; p.Kt = a->KH * a->KW * p.Cin;
     const int es = a->dtype == DDPM_F32 ? 4 : 2;
     p.vecA = (p.Cin % 4 == 0) && (a->in.pitch % 4 == 0) && al(a->in.ptr, 4 * es);
@@ -213,7 +213,7 @@ struct WgP {
     TV act, dy;
     float* dw;
     int KH, KW, stride, pad, a_silu;
-    int Cin, Cout, Q, Kf, HoWo, qper;
+    int Cin, Cout, Q, Kf, HoWo, qper, CinV, CoutV;
     int vecA, vecY;
 };
 
@@ -308,13 +308,14 @@ __global__ void __launch_bounds__(CT) wgrad_simt_kernel(WgP p) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         int co = co0 + ty * 4 + i;
-        if (co >= p.Cout) continue;
+        if (co >= p.Cout || co >= p.CoutV) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             int kf = kf0 + tx * 4 + j;
             if (kf >= p.Kf) continue;
             int tp = kf / p.Cin, c = kf - tp * p.Cin;
-            atomicAdd(&p.dw[((int64_t)co * p.Cin + c) * taps + tp], acc[i][j]);
+            if (c >= p.CinV) continue;
+            atomicAdd(&p.dw[((int64_t)co * p.CinV + c) * taps + tp], acc[i][j]);
         }
     }
 }
@@ -324,6 +325,7 @@ int wgrad_simt_launch(const ddpm_wgrad_args* a, cudaStream_t st) {
     p.act = TV(a->act); p.dy = TV(a->dy); p.dw = a->dw;
     p.KH = a->KH; p.KW = a->KW; p.stride = a->stride; p.pad = a->pad; p.a_silu = a->a_silu;
     p.Cin = a->act.C; p.Cout = a->dy.C;
+    p.CinV = a->cin_valid > 0 ? a->cin_valid : p.Cin; p.CoutV = a->cout_valid > 0 ? a->cout_valid : p.Cout;
     p.HoWo = a->dy.H * a->dy.W; p.Q = a->dy.N * p.HoWo; p.Kf = a->KH * a->KW * p.Cin;
     const int es = a->dtype == DDPM_F32 ? 4 : 2;
     p.vecA = (p.Cin % 4 == 0) && (a->act.pitch % 4 == 0) && al(a->act.ptr, 4 * es);

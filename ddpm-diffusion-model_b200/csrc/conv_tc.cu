@@ -110,7 +110,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 // ------------------------------------------------------------------------------------------------
 struct TcParams {
     TV out, res;
-    const float* bias; const float* tbias; int tbias_pitch;
+    const float* bias; const float* tbias; int tbias_pitch; int bias_n;
     int Cin, Cout, NT;          // NT: output-channel tile (UMMA N), multiple of 16, <= 256
     int taps, tpb;              // 9 (3x3) or 1; taps per B stage (3 or 1)
     int Hp, Wp, H, W, Qtot;     // padded geometry shared by input and output
@@ -120,6 +120,7 @@ struct TcParams {
     int tmem_cols;              // power of two >= MT*NT
     int has_res, accum;
     int baseoff;
+    int sub;                    // 1: stride-2 conv = stride-1 conv kept at even (y, x) only
 };
 
 template <int MT, bool SW32>
@@ -239,6 +240,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                 n = Q / HpWp; int r = Q - n * HpWp; int yp = r / p.Wp; int xp = r - yp * p.Wp;
                 y = yp - 1; x = xp - 1;
                 valid = y >= 0 && y < p.H && x >= 0 && x < p.W;
+                if (p.sub) { valid = valid && ((y | x) & 1) == 0; y >>= 1; x >>= 1; }
             }
             bf16* orow = valid ? p.out.at<bf16>(n, y, x, n0) : nullptr;
             const bf16* rrow = (valid && p.has_res) ? p.res.at<bf16>(n, y, x, n0) : nullptr;
@@ -254,7 +256,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
                     if (p.bias) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + n0 + c0 + i);
+                        for (int i = 0; i < 16; ++i) if (n0 + c0 + i < p.bias_n) v[i] += __ldg(p.bias + n0 + c0 + i);
                     }
                     if (tb) {
 #pragma unroll
@@ -331,10 +333,13 @@ static int pick_nt(int Cout) {
 }
 
 int conv_tc_supported(const ddpm_conv_args* a) {
-    if (a->dtype != DDPM_BF16 || a->mode != DDPM_CONV_NORMAL || a->stride != 1 || a->a_silu || a->z.ptr) return 0;
+    if (a->dtype != DDPM_BF16 || a->mode != DDPM_CONV_NORMAL || a->a_silu || a->z.ptr) return 0;
     if (!((a->KH == 3 && a->KW == 3 && a->pad == 1) || (a->KH == 1 && a->KW == 1 && a->pad == 0))) return 0;
     const ddpm_tensor &in = a->in, &out = a->out;
-    if (in.halo != 1 || out.halo != 1 || in.H != out.H || in.W != out.W || in.N != out.N) return 0;
+    if (in.halo != 1 || out.halo != 1 || in.N != out.N) return 0;
+    if (a->stride == 1) { if (in.H != out.H || in.W != out.W) return 0; }
+    else if (a->stride == 2) { if (a->KH != 3 || (in.H & 1) || (in.W & 1) || out.H * 2 != in.H || out.W * 2 != in.W) return 0; }
+    else return 0;
     if (in.C % 16 || out.C % 16 || in.pitch % 8 || out.pitch % 8) return 0;
     if (((uintptr_t)in.ptr & 15) || ((uintptr_t)out.ptr & 15) || ((uintptr_t)a->w & 15)) return 0;
     if (a->res.ptr && (a->res.halo != 1 || a->res.pitch % 8 || ((uintptr_t)a->res.ptr & 15))) return 0;
@@ -362,12 +367,14 @@ int conv_tc_launch(const ddpm_conv_args* a, cudaStream_t st) {
     p.out = TV(a->out);
     p.has_res = a->res.ptr != nullptr; p.res = p.has_res ? TV(a->res) : TV(a->out);
     p.bias = a->bias; p.tbias = a->tbias; p.tbias_pitch = a->tbias_pitch;
+    p.bias_n = a->bias_n > 0 ? a->bias_n : a->out.C;
     p.Cin = a->in.C; p.Cout = a->out.C; p.NT = pick_nt(p.Cout);
     p.taps = a->KH * a->KW; p.tpb = p.taps == 9 ? 3 : 1;
     p.Hp = a->in.H + 2; p.Wp = a->in.W + 2; p.H = a->in.H; p.W = a->in.W;
     p.Qtot = a->in.N * p.Hp * p.Wp;
     p.accum = (a->epi & DDPM_EPI_ACCUM) ? 1 : 0;
     p.baseoff = g_tc_baseoff;
+    p.sub = a->stride == 2 ? 1 : 0;
     int MT = 256 / p.NT; if (MT >= 2) MT = 2; if (MT < 1) MT = 1;
     int halo_rows = p.taps == 9 ? p.Wp + 1 : 0;
     {
@@ -412,5 +419,213 @@ int conv_tc_launch(const ddpm_conv_args* a, cudaStream_t st) {
     return sw32 ? launch<1, true>(tmA, tmB, p, grid, smem, st) : launch<1, false>(tmA, tmB, p, grid, smem, st);
 }
 
-int wgrad_tc_supported(const ddpm_wgrad_args*) { return 0; }
-int wgrad_tc_launch(const ddpm_wgrad_args*, cudaStream_t) { return DDPM_E_ARG; }
+// ================================================================================================
+// weight gradient:  dW[co][ci][ky][kx] += sum_Q dY[Q][co] * A[Q + (ky-1)*Wp + (kx-1)][ci]
+//
+// The reduction runs over padded-linear pixels Q (dY's halo is zero, so halo rows contribute 0), which
+// makes BOTH operands "MN-major" (channels contiguous, K = pixels strided): dY tiles [64 px][128 co]
+// and activation patches [64+2 px][NT ci] are TMA-loaded with SWIZZLE_128B and fed to tcgen05.mma with
+// a_major = b_major = MN.  A CTA owns one filter row ky (three taps = three row-shifted descriptors of
+// the same patch, accumulators D[128 co][3*NT] in TMEM), one ci tile, one co tile and one slice of the
+// pixel range (split-K).  Partials go to a workspace with coalesced stores and a second kernel reduces
+// them into the fp32 OIHW gradient (no atomics).
+// ================================================================================================
+int wgrad_tc_supported(const ddpm_wgrad_args* a);
+#define WG_KQ 64          // pixels per pipeline stage (4 UMMA K-steps)
+#define WG_ROWS 72        // patch rows per stage (KQ + 2 shifts, rounded to 8)
+#define WG_STAGES 5
+
+struct WgTcParams {
+    float* ws;                  // [split][mtile][grp][128][3*NT]
+    int Cin, Cout, NT, n_tiles, m_tiles;
+    int Wp, Qtot, stages_total, stages_per_cta;
+    int nblkA;                  // 64-channel blocks per activation patch (1 or 2)
+    int stage_bytes, tmem_cols;
+    int ntap;                   // taps per CTA: 3 (one filter row of a 3x3) or 1 (1x1)
+    int CinV, CoutV;            // unpadded channel counts of the fp32 gradient
+};
+
+__global__ void __launch_bounds__(TC_THREADS) wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY,
+                                                               const __grid_constant__ CUtensorMap tmA, WgTcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = (uint64_t*)(smem + (size_t)WG_STAGES * p.stage_bytes);
+    uint64_t* empty = full + WG_STAGES;
+    uint64_t* acc_full = empty + WG_STAGES;
+    uint32_t* tmem_slot = (uint32_t*)(acc_full + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int split = blockIdx.x, grp = blockIdx.y, mtile = blockIdx.z;
+    const int ky = grp / p.n_tiles, ntile = grp - ky * p.n_tiles;
+    const int m0 = mtile * 128, n0 = ntile * p.NT;
+    const int s_beg = split * p.stages_per_cta;
+    const int s_end = min(p.stages_total, s_beg + p.stages_per_cta);
+    const int nst = max(0, s_end - s_beg);
+    const int y_bytes = 2 * WG_KQ * 128;                 // two 64-channel blocks of dY
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < WG_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = 0; i < nst; ++i) {
+                const int s = i % WG_STAGES; const uint32_t ph = (i / WG_STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                uint8_t* dst = smem + (size_t)s * p.stage_bytes;
+                mbar_expect_tx(&full[s], (uint32_t)(y_bytes + p.nblkA * WG_ROWS * 128));
+                const int Q = (s_beg + i) * WG_KQ;
+                tma_load_2d(dst, &tmY, &full[s], m0, Q);
+                tma_load_2d(dst + WG_KQ * 128, &tmY, &full[s], m0 + 64, Q);
+                const int rowA = p.ntap == 3 ? Q + (ky - 1) * p.Wp - 1 : Q;
+                for (int b = 0; b < p.nblkA; ++b)
+                    tma_load_2d(dst + y_bytes + (size_t)b * WG_ROWS * 128, &tmA, &full[s], n0 + 64 * b, rowA);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // a_major = b_major = MN (bits 15, 16); M = 128; N = NT
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                                   ((uint32_t)(p.NT >> 3) << 17) | ((128u >> 4) << 24);
+            for (int i = 0; i < nst; ++i) {
+                const int s = i % WG_STAGES; const uint32_t ph = (i / WG_STAGES) & 1;
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint32_t ybase = smem_u32(smem + (size_t)s * p.stage_bytes);
+                const uint32_t abase = ybase + (uint32_t)y_bytes;
+#pragma unroll
+                for (int ks = 0; ks < WG_KQ / 16; ++ks) {
+                    const uint64_t ydesc = make_desc(ybase + (uint32_t)(ks * 16 * 128), (uint32_t)(WG_KQ * 128), 1024u, 2u, 0);
+                    for (int kx = 0; kx < p.ntap; ++kx) {
+                        const uint64_t adesc = make_desc(abase + (uint32_t)((ks * 16 + kx) * 128), (uint32_t)(WG_ROWS * 128), 1024u, 2u, 0);
+                        umma_bf16(tmem_base + (uint32_t)(kx * p.NT), ydesc, adesc, idesc, (i | ks) != 0 ? 1u : 0u);
+                    }
+                }
+                umma_commit(&empty[s]);
+            }
+            umma_commit(acc_full);
+        }
+    } else {
+        const int qd = warp & 3;
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        const int cols = p.ntap * p.NT;
+        float* dst = p.ws + ((((size_t)split * p.m_tiles + mtile) * gridDim.y + grp) * 128 + qd * 32 + lane) * cols;
+#pragma unroll 1
+        for (int c0 = 0; c0 < cols; c0 += 16) {
+            uint32_t r[16];
+            if (nst > 0) {
+                tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)c0, r);
+                tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) r[i] = 0u;
+            }
+#pragma unroll
+            for (int i = 0; i < 16; i += 4)
+                *reinterpret_cast<uint4*>(dst + c0 + i) = make_uint4(r[i], r[i + 1], r[i + 2], r[i + 3]);
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
+}
+
+// dw[co][ci][ky][kx] += sum_split ws[split][mtile][ky*n_tiles+ntile][co%128][kx*NT + ci%NT]
+__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int splits, WgTcParams p) {
+    const int taps = p.ntap * p.ntap;
+    const int total = p.CoutV * taps * p.CinV;
+    const int grps = p.ntap * p.n_tiles, cols = p.ntap * p.NT;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        // enumerate (co, tap, ci) with ci fastest so workspace reads are coalesced
+        int ci = i % p.CinV; int r = i / p.CinV; int tap = r % taps; int co = r / taps;
+        int ky = tap / p.ntap, kx = tap - ky * p.ntap;
+        int mtile = co >> 7, ntile = ci / p.NT;
+        size_t off = ((((size_t)mtile) * grps + ky * p.n_tiles + ntile) * 128 + (co & 127)) * cols + kx * p.NT + (ci - ntile * p.NT);
+        size_t stride = (size_t)p.m_tiles * grps * 128 * cols;
+        float acc = 0.f;
+        for (int s = 0; s < splits; ++s) acc += ws[off + s * stride];
+        dw[((size_t)co * p.CinV + ci) * taps + tap] += acc;
+    }
+}
+
+static int wg_pick_nt(int Cin) {
+    for (int nt = 128; nt >= 16; nt -= 16) if (Cin % nt == 0) return nt;
+    return 0;
+}
+
+static void wg_plan(const ddpm_wgrad_args* a, WgTcParams* p, int* splits) {
+    p->Cin = a->act.C; p->Cout = a->dy.C; p->NT = wg_pick_nt(p->Cin);
+    p->ntap = a->KH == 3 ? 3 : 1;
+    p->CinV = a->cin_valid > 0 ? a->cin_valid : p->Cin; p->CoutV = a->cout_valid > 0 ? a->cout_valid : p->Cout;
+    p->n_tiles = p->Cin / p->NT; p->m_tiles = (p->Cout + 127) / 128;
+    p->Wp = a->act.W + 2; p->Qtot = a->act.N * (a->act.H + 2) * p->Wp;
+    p->stages_total = (p->Qtot + WG_KQ - 1) / WG_KQ;
+    p->nblkA = (p->NT + 63) / 64;
+    p->stage_bytes = 2 * WG_KQ * 128 + p->nblkA * WG_ROWS * 128;
+    p->tmem_cols = 32; while (p->tmem_cols < p->ntap * p->NT) p->tmem_cols <<= 1;
+    int yz = p->ntap * p->n_tiles * p->m_tiles;
+    int sp = (148 + yz - 1) / yz;
+    int max_sp = (p->stages_total + 7) / 8; if (max_sp < 1) max_sp = 1;
+    if (sp > max_sp) sp = max_sp;
+    if (sp < 1) sp = 1;
+    p->stages_per_cta = (p->stages_total + sp - 1) / sp;
+    *splits = (p->stages_total + p->stages_per_cta - 1) / p->stages_per_cta;
+}
+
+extern "C" int64_t ddpm_wgrad_workspace_bytes(const ddpm_wgrad_args* a) {
+    if (!a || !wgrad_tc_supported(a)) return 0;
+    WgTcParams p; int splits; wg_plan(a, &p, &splits);
+    return (int64_t)splits * p.m_tiles * p.ntap * p.n_tiles * 128 * p.ntap * p.NT * 4;
+}
+
+int wgrad_tc_supported(const ddpm_wgrad_args* a) {
+    if (a->dtype != DDPM_BF16 || a->stride != 1 || a->a_silu) return 0;
+    if (!((a->KH == 3 && a->KW == 3 && a->pad == 1) || (a->KH == 1 && a->KW == 1 && a->pad == 0))) return 0;
+    const ddpm_tensor &x = a->act, &y = a->dy;
+    if (x.halo != 1 || y.halo != 1 || x.H != y.H || x.W != y.W || x.N != y.N) return 0;
+    if (x.C % 16 || y.C % 8 || x.pitch % 8 || y.pitch % 8) return 0;
+    if (((uintptr_t)x.ptr & 15) || ((uintptr_t)y.ptr & 15)) return 0;
+    if (wg_pick_nt(x.C) == 0) return 0;
+    if ((int64_t)x.N * (x.H + 2) * (x.W + 2) < 8 * WG_KQ) return 0;      // tiny problems: CUDA cores
+    return 1;
+}
+
+int wgrad_tc_launch(const ddpm_wgrad_args* a, cudaStream_t st) {
+    int rc = get_encode(); if (rc) return rc;
+    WgTcParams p; int splits; wg_plan(a, &p, &splits);
+    int64_t need = (int64_t)splits * p.m_tiles * p.ntap * p.n_tiles * 128 * p.ntap * p.NT * 4;
+    if (!a->workspace || a->workspace_bytes < need) return DDPM_E_ARG;
+    p.ws = (float*)a->workspace;
+    CUtensorMap tmY, tmA;
+    {
+        uint64_t d[2] = {(uint64_t)p.Cout, (uint64_t)p.Qtot}; uint64_t s[1] = {(uint64_t)a->dy.pitch * 2};
+        uint32_t b[2] = {64, WG_KQ};
+        if (encode(&tmY, a->dy.ptr, 2, d, s, b, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+    }
+    {
+        uint64_t d[2] = {(uint64_t)p.Cin, (uint64_t)p.Qtot}; uint64_t s[1] = {(uint64_t)a->act.pitch * 2};
+        uint32_t b[2] = {64, WG_ROWS};
+        if (encode(&tmA, a->act.ptr, 2, d, s, b, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+    }
+    size_t smem = (size_t)WG_STAGES * p.stage_bytes + 8 * (2 * WG_STAGES + 1) + 16 + 1024;
+    static size_t configured = 0;
+    if (smem > configured) {
+        CUDA_TRY(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    dim3 grid(splits, p.ntap * p.n_tiles, p.m_tiles);
+    wgrad_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmY, tmA, p);
+    LAUNCH_OK();
+    int total = p.CoutV * p.ntap * p.ntap * p.CinV;
+    int rg = (total + 255) / 256; if (rg > 148 * 8) rg = 148 * 8;
+    wgrad_reduce_kernel<<<rg, 256, 0, st>>>(p.ws, a->dw, splits, p);
+    LAUNCH_OK();
+    return 0;
+}

@@ -434,29 +434,30 @@ extern "C" int ddpm_to_image01(const float* x, float* out, int64_t n, void* stre
 
 // ---------------------------------------------------------------- layout conversion
 template <typename TS, typename TD, bool TO_NHWC>
-__global__ void layout_kernel(char* nchw, int64_t sn, int64_t sc, int64_t sh, int64_t sw, TV v) {
+__global__ void layout_kernel(char* nchw, int64_t sn, int64_t sc, int64_t sh, int64_t sw, TV v, int srcC) {
     int64_t total = (int64_t)v.N * v.H * v.W * v.C;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int c = (int)(i % v.C); int64_t r = i / v.C;
         int x = (int)(r % v.W); r /= v.W;
         int y = (int)(r % v.H); int n = (int)(r / v.H);
         int64_t off = n * sn + c * sc + y * sh + x * sw;
-        if (TO_NHWC) stf<TD>(v.at<TD>(n, y, x, c), ldf<TS>(reinterpret_cast<const TS*>(nchw) + off));
+        if (TO_NHWC) stf<TD>(v.at<TD>(n, y, x, c), c < srcC ? ldf<TS>(reinterpret_cast<const TS*>(nchw) + off) : 0.f);
         else stf<TD>(reinterpret_cast<TD*>(nchw) + off, ldf<TS>(v.at<TS>(n, y, x, c)));
     }
 }
 
-extern "C" int ddpm_nchw_to_nhwc(const void* src, int src_dtype, int64_t sn, int64_t sc, int64_t sh,
+extern "C" int ddpm_nchw_to_nhwc(const void* src, int src_dtype, int src_C, int64_t sn, int64_t sc, int64_t sh,
                                  int64_t sw, const ddpm_tensor* dst, int dst_dtype, void* stream) {
-    if (!src || !tensor_ok(dst)) return DDPM_E_ARG;
+    if (!src || !tensor_ok(dst) || src_C <= 0 || src_C > dst->C) return DDPM_E_ARG;
+    const int srcC = src_C;
     TV v(*dst); cudaStream_t st = (cudaStream_t)stream;
     int64_t total = (int64_t)v.N * v.H * v.W * v.C;
     int grid = (int)((total + 255) / 256); if (grid > 148 * 16) grid = 148 * 16;
     char* s = (char*)src;
-    if (src_dtype == DDPM_F32 && dst_dtype == DDPM_F32) layout_kernel<float, float, true><<<grid, 256, 0, st>>>(s, sn, sc, sh, sw, v);
-    else if (src_dtype == DDPM_F32 && dst_dtype == DDPM_BF16) layout_kernel<float, bf16, true><<<grid, 256, 0, st>>>(s, sn, sc, sh, sw, v);
-    else if (src_dtype == DDPM_BF16 && dst_dtype == DDPM_BF16) layout_kernel<bf16, bf16, true><<<grid, 256, 0, st>>>(s, sn, sc, sh, sw, v);
-    else if (src_dtype == DDPM_BF16 && dst_dtype == DDPM_F32) layout_kernel<bf16, float, true><<<grid, 256, 0, st>>>(s, sn, sc, sh, sw, v);
+    if (src_dtype == DDPM_F32 && dst_dtype == DDPM_F32) layout_kernel<float, float, true><<<grid, 256, 0, st>>>(s, sn, sc, sh, sw, v, srcC);
+    else if (src_dtype == DDPM_F32 && dst_dtype == DDPM_BF16) layout_kernel<float, bf16, true><<<grid, 256, 0, st>>>(s, sn, sc, sh, sw, v, srcC);
+    else if (src_dtype == DDPM_BF16 && dst_dtype == DDPM_BF16) layout_kernel<bf16, bf16, true><<<grid, 256, 0, st>>>(s, sn, sc, sh, sw, v, srcC);
+    else if (src_dtype == DDPM_BF16 && dst_dtype == DDPM_F32) layout_kernel<bf16, float, true><<<grid, 256, 0, st>>>(s, sn, sc, sh, sw, v, srcC);
     else return DDPM_E_ARG;
     LAUNCH_OK();
     return 0;
@@ -469,10 +470,10 @@ extern "C" int ddpm_nhwc_to_nchw(const ddpm_tensor* src, int src_dtype, void* ds
     int64_t total = (int64_t)v.N * v.H * v.W * v.C;
     int grid = (int)((total + 255) / 256); if (grid > 148 * 16) grid = 148 * 16;
     char* d = (char*)dst;
-    if (src_dtype == DDPM_F32 && dst_dtype == DDPM_F32) layout_kernel<float, float, false><<<grid, 256, 0, st>>>(d, sn, sc, sh, sw, v);
-    else if (src_dtype == DDPM_BF16 && dst_dtype == DDPM_F32) layout_kernel<bf16, float, false><<<grid, 256, 0, st>>>(d, sn, sc, sh, sw, v);
-    else if (src_dtype == DDPM_BF16 && dst_dtype == DDPM_BF16) layout_kernel<bf16, bf16, false><<<grid, 256, 0, st>>>(d, sn, sc, sh, sw, v);
-    else if (src_dtype == DDPM_F32 && dst_dtype == DDPM_BF16) layout_kernel<float, bf16, false><<<grid, 256, 0, st>>>(d, sn, sc, sh, sw, v);
+    if (src_dtype == DDPM_F32 && dst_dtype == DDPM_F32) layout_kernel<float, float, false><<<grid, 256, 0, st>>>(d, sn, sc, sh, sw, v, v.C);
+    else if (src_dtype == DDPM_BF16 && dst_dtype == DDPM_F32) layout_kernel<bf16, float, false><<<grid, 256, 0, st>>>(d, sn, sc, sh, sw, v, v.C);
+    else if (src_dtype == DDPM_BF16 && dst_dtype == DDPM_BF16) layout_kernel<bf16, bf16, false><<<grid, 256, 0, st>>>(d, sn, sc, sh, sw, v, v.C);
+    else if (src_dtype == DDPM_F32 && dst_dtype == DDPM_BF16) layout_kernel<float, bf16, false><<<grid, 256, 0, st>>>(d, sn, sc, sh, sw, v, v.C);
     else return DDPM_E_ARG;
     LAUNCH_OK();
     return 0;

@@ -47,7 +47,7 @@ static inline bool vec_ok(const ddpm_tensor* t, int vec, int esz) {
     return (t->C % vec) == 0 && (t->pitch % vec) == 0 && ((((uintptr_t)t->ptr) % (vec * esz)) == 0);
 }
 static inline int blocks_per_image(int N, int HW, int ppi) {
-    int want = (148 * 4 + N - 1) / N;
+    int want = (148 * 16 + N - 1) / N;
     int maxb = (HW + ppi - 1) / ppi;
     if (want < 1) want = 1;
     return want < maxb ? want : maxb;
@@ -55,7 +55,7 @@ static inline int blocks_per_image(int N, int HW, int ppi) {
 
 // ------------------------------------------------------------------------------------ gn_stats
 template <typename T, int VEC>
-__global__ void __launch_bounds__(NT) gn_stats_kernel(TV x, int G, double* stats) {
+__global__ void __launch_bounds__(NT, 4) gn_stats_kernel(TV x, int G, double* stats) {
     extern __shared__ double sg[];          // [G][2]
     const int n = blockIdx.y, cpg = x.C / G;
     for (int i = threadIdx.x; i < 2 * G; i += NT) sg[i] = 0.0;
@@ -120,7 +120,7 @@ __device__ __forceinline__ void group_moments(const double* stats, int n, int G,
 
 // ------------------------------------------------------------------------------------ gn_apply
 template <typename T, int VEC>
-__global__ void __launch_bounds__(NT) gn_apply_kernel(TV x, TV o, int G, const double* stats, const float* gamma,
+__global__ void __launch_bounds__(NT, 4) gn_apply_kernel(TV x, TV o, int G, const double* stats, const float* gamma,
                                                       const float* beta, float eps, int act, float p_drop,
                                                       const uint64_t* rng, uint32_t layer) {
     extern __shared__ float tb[];            // scale[C], shift[C]
@@ -141,21 +141,29 @@ __global__ void __launch_bounds__(NT) gn_apply_kernel(TV x, TV o, int G, const d
     const float keep_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
     const int per = (HW + gridDim.x - 1) / gridDim.x;
     const int p0 = blockIdx.x * per, p1 = min(HW, p0 + per);
-    for (int p = p0 + m.prow; p < p1; p += m.ppi) {
-        int y = p / x.W, xx = p - y * x.W;
-        float v[VEC];
-        ldv<T, VEC>(x.at<T>(n, y, xx, m.cv * VEC), v);
+    constexpr int U = 2;
+    for (int pb = p0 + m.prow; pb < p1; pb += U * m.ppi) {
+        float v[U][VEC];
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-            float z = fmaf(v[i], sc[i], sh[i]);
-            if (act) z = silu_f(z);
-            if (p_drop > 0.f) {
-                uint64_t e = ((uint64_t)n * HW + p) * C + m.cv * VEC + i;
-                z = dropout_keep(rng, layer, e, p_drop) ? z * keep_scale : 0.f;
-            }
-            v[i] = z;
+        for (int u = 0; u < U; ++u) {
+            int p = pb + u * m.ppi;
+            if (p < p1) { int y = p / x.W, xx = p - y * x.W; ldv<T, VEC>(x.at<T>(n, y, xx, m.cv * VEC), v[u]); }
         }
-        stv<T, VEC>(o.at<T>(n, y, xx, m.cv * VEC), v);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            int p = pb + u * m.ppi;
+            if (p >= p1) break;
+            uint32_t keep = 0xffffffffu;
+            if (p_drop > 0.f) keep = dropout_mask<VEC>(rng, layer, ((uint64_t)n * HW + p) * C + m.cv * VEC, p_drop);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                float z = fmaf(v[u][i], sc[i], sh[i]);
+                if (act) z = silu_f(z);
+                v[u][i] = ((keep >> i) & 1u) ? z * keep_scale : 0.f;
+            }
+            int y = p / x.W, xx = p - y * x.W;
+            stv<T, VEC>(o.at<T>(n, y, xx, m.cv * VEC), v[u]);
+        }
     }
 }
 
@@ -185,50 +193,47 @@ extern "C" int ddpm_gn_apply(const ddpm_tensor* x, int dtype, int groups, const 
 // z = x*scale+shift, y = drop(act(z)).  dz = dy * mask/(1-p) * act'(z).
 // pass 1: ws[n][c] = (sum_p dz, sum_p dz*xhat).
 template <typename T, int VEC>
-__global__ void __launch_bounds__(NT) gn_bwd_reduce_kernel(TV x, TV dy, int G, const double* stats, const float* gamma,
-                                                           const float* beta, float eps, int act, float p_drop,
-                                                           const uint64_t* rng, uint32_t layer, float* ws) {
-    extern __shared__ float tb[];            // mean_rstd: rs[C], mr[C] ; acc: s1[C], s2[C]
+__global__ void __launch_bounds__(NT, 4) gn_bwd_reduce_kernel(TV x, TV dy, int G, const double* stats, const float* gamma,
+                                                              const float* beta, float eps, int act, float p_drop,
+                                                              const uint64_t* rng, uint32_t layer, float* ws) {
+    extern __shared__ float tb[];            // rs[C], mr[C], ga[C], be[C], s1[C], s2[C]
     const int n = blockIdx.y, C = x.C, cpg = C / G, HW = x.H * x.W;
-    float* rsv = tb; float* mrv = tb + C; float* a1 = tb + 2 * C; float* a2 = tb + 3 * C;
+    float* rsv = tb; float* mrv = tb + C; float* gav = tb + 2 * C; float* bev = tb + 3 * C;
+    float* a1 = tb + 4 * C; float* a2 = tb + 5 * C;
     for (int c = threadIdx.x; c < C; c += NT) {
         float mu, rs;
         group_moments(stats, n, G, c / cpg, (double)cpg * HW, eps, &mu, &rs);
-        rsv[c] = rs; mrv[c] = mu * rs; a1[c] = 0.f; a2[c] = 0.f;
+        rsv[c] = rs; mrv[c] = mu * rs; gav[c] = gamma[c]; bev[c] = beta[c]; a1[c] = 0.f; a2[c] = 0.f;
     }
     __syncthreads();
     PixMap m = make_map<VEC>(C);
     if (m.active) {
-        float rs[VEC], mr[VEC], ga[VEC], be[VEC], s1[VEC], s2[VEC];
+        float s1[VEC], s2[VEC];
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-            int c = m.cv * VEC + i;
-            rs[i] = rsv[c]; mr[i] = mrv[c]; ga[i] = gamma[c]; be[i] = beta[c]; s1[i] = 0.f; s2[i] = 0.f;
-        }
+        for (int i = 0; i < VEC; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+        const int c0 = m.cv * VEC;
         const float keep_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
         const int per = (HW + gridDim.x - 1) / gridDim.x;
         const int p0 = blockIdx.x * per, p1 = min(HW, p0 + per);
         for (int p = p0 + m.prow; p < p1; p += m.ppi) {
             int y = p / x.W, xx = p - y * x.W;
             float v[VEC], d[VEC];
-            ldv<T, VEC>(x.at<T>(n, y, xx, m.cv * VEC), v);
-            ldv<T, VEC>(dy.at<T>(n, y, xx, m.cv * VEC), d);
+            ldv<T, VEC>(x.at<T>(n, y, xx, c0), v);
+            ldv<T, VEC>(dy.at<T>(n, y, xx, c0), d);
+            uint32_t keep = 0xffffffffu;
+            if (p_drop > 0.f) keep = dropout_mask<VEC>(rng, layer, ((uint64_t)n * HW + p) * C + c0, p_drop);
 #pragma unroll
             for (int i = 0; i < VEC; ++i) {
-                float xh = fmaf(v[i], rs[i], -mr[i]);
-                float dz = d[i];
-                if (p_drop > 0.f) {
-                    uint64_t e = ((uint64_t)n * HW + p) * C + m.cv * VEC + i;
-                    dz = dropout_keep(rng, layer, e, p_drop) ? dz * keep_scale : 0.f;
-                }
-                if (act) dz *= dsilu_f(fmaf(xh, ga[i], be[i]));
-                s1[i] += dz; s2[i] += dz * xh;
+                float xh = fmaf(v[i], rsv[c0 + i], -mrv[c0 + i]);
+                float dz = ((keep >> i) & 1u) ? d[i] * keep_scale : 0.f;
+                if (act) dz *= dsilu_f(fmaf(xh, gav[c0 + i], bev[c0 + i]));
+                s1[i] += dz; s2[i] = fmaf(dz, xh, s2[i]);
             }
         }
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
-            atomicAdd(&a1[m.cv * VEC + i], s1[i]);
-            atomicAdd(&a2[m.cv * VEC + i], s2[i]);
+            atomicAdd(&a1[c0 + i], s1[i]);
+            atomicAdd(&a2[c0 + i], s2[i]);
         }
     }
     __syncthreads();
@@ -240,18 +245,14 @@ __global__ void __launch_bounds__(NT) gn_bwd_reduce_kernel(TV x, TV dy, int G, c
 
 // pass 2: dx = rstd * (dz*gamma - A_g - xhat*B_g),  A_g = mean_g(gamma*S1), B_g = mean_g(gamma*S2)
 template <typename T, int VEC>
-__global__ void __launch_bounds__(NT) gn_bwd_apply_kernel(TV x, TV dy, TV dx, int G, const double* stats,
-                                                          const float* gamma, const float* beta, float eps, int act,
-                                                          float p_drop, const uint64_t* rng, uint32_t layer,
-                                                          const float* ws, int accumulate) {
-    extern __shared__ float tb[];            // rs[C], mr[C], ag[G], bg[G]
+__global__ void __launch_bounds__(NT, 4) gn_bwd_apply_kernel(TV x, TV dy, TV dx, int G, const double* stats,
+                                                             const float* gamma, const float* beta, float eps, int act,
+                                                             float p_drop, const uint64_t* rng, uint32_t layer,
+                                                             const float* ws, int accumulate) {
+    extern __shared__ float tb[];            // rs[C], mr[C], ga[C], be[C], ra[C] (= rs*A_g), rb[C] (= rs*B_g), ag[G], bg[G]
     const int n = blockIdx.y, C = x.C, cpg = C / G, HW = x.H * x.W;
-    float* rsv = tb; float* mrv = tb + C; float* ag = tb + 2 * C; float* bg = ag + G;
-    for (int c = threadIdx.x; c < C; c += NT) {
-        float mu, rs;
-        group_moments(stats, n, G, c / cpg, (double)cpg * HW, eps, &mu, &rs);
-        rsv[c] = rs; mrv[c] = mu * rs;
-    }
+    float* rsv = tb; float* mrv = tb + C; float* gav = tb + 2 * C; float* bev = tb + 3 * C;
+    float* rav = tb + 4 * C; float* rbv = tb + 5 * C; float* ag = tb + 6 * C; float* bg = ag + G;
     for (int g = threadIdx.x; g < G; g += NT) {
         float a = 0.f, b = 0.f;
         for (int j = 0; j < cpg; ++j) {
@@ -263,37 +264,37 @@ __global__ void __launch_bounds__(NT) gn_bwd_apply_kernel(TV x, TV dy, TV dx, in
         ag[g] = a * inv; bg[g] = b * inv;
     }
     __syncthreads();
+    for (int c = threadIdx.x; c < C; c += NT) {
+        float mu, rs;
+        group_moments(stats, n, G, c / cpg, (double)cpg * HW, eps, &mu, &rs);
+        rsv[c] = rs; mrv[c] = mu * rs; gav[c] = gamma[c]; bev[c] = beta[c];
+        rav[c] = rs * ag[c / cpg]; rbv[c] = rs * bg[c / cpg];
+    }
+    __syncthreads();
     PixMap m = make_map<VEC>(C);
     if (!m.active) return;
-    float rs[VEC], mr[VEC], ga[VEC], be[VEC], A[VEC], Bq[VEC];
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-        int c = m.cv * VEC + i;
-        rs[i] = rsv[c]; mr[i] = mrv[c]; ga[i] = gamma[c]; be[i] = beta[c];
-        A[i] = ag[c / cpg]; Bq[i] = bg[c / cpg];
-    }
+    const int c0 = m.cv * VEC;
     const float keep_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
     const int per = (HW + gridDim.x - 1) / gridDim.x;
     const int p0 = blockIdx.x * per, p1 = min(HW, p0 + per);
     for (int p = p0 + m.prow; p < p1; p += m.ppi) {
         int y = p / x.W, xx = p - y * x.W;
         float v[VEC], d[VEC], r[VEC];
-        ldv<T, VEC>(x.at<T>(n, y, xx, m.cv * VEC), v);
-        ldv<T, VEC>(dy.at<T>(n, y, xx, m.cv * VEC), d);
-        if (accumulate) ldv<T, VEC>(dx.at<T>(n, y, xx, m.cv * VEC), r);
+        ldv<T, VEC>(x.at<T>(n, y, xx, c0), v);
+        ldv<T, VEC>(dy.at<T>(n, y, xx, c0), d);
+        if (accumulate) ldv<T, VEC>(dx.at<T>(n, y, xx, c0), r);
+        uint32_t keep = 0xffffffffu;
+        if (p_drop > 0.f) keep = dropout_mask<VEC>(rng, layer, ((uint64_t)n * HW + p) * C + c0, p_drop);
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
-            float xh = fmaf(v[i], rs[i], -mr[i]);
-            float dz = d[i];
-            if (p_drop > 0.f) {
-                uint64_t e = ((uint64_t)n * HW + p) * C + m.cv * VEC + i;
-                dz = dropout_keep(rng, layer, e, p_drop) ? dz * keep_scale : 0.f;
-            }
-            if (act) dz *= dsilu_f(fmaf(xh, ga[i], be[i]));
-            float g = rs[i] * (dz * ga[i] - A[i] - xh * Bq[i]);
+            float rs = rsv[c0 + i], ga = gav[c0 + i];
+            float xh = fmaf(v[i], rs, -mrv[c0 + i]);
+            float dz = ((keep >> i) & 1u) ? d[i] * keep_scale : 0.f;
+            if (act) dz *= dsilu_f(fmaf(xh, ga, bev[c0 + i]));
+            float g = fmaf(dz * ga, rs, -rav[c0 + i]) - xh * rbv[c0 + i];     // rs*(dz*ga - A - xh*B)
             r[i] = accumulate ? r[i] + g : g;
         }
-        stv<T, VEC>(dx.at<T>(n, y, xx, m.cv * VEC), r);
+        stv<T, VEC>(dx.at<T>(n, y, xx, c0), r);
     }
 }
 
@@ -319,9 +320,9 @@ extern "C" int ddpm_gn_bwd(const ddpm_tensor* x, int dtype, int groups, const do
     int HW = x->H * x->W, C = x->C;
 #define GO(T, VEC) { int cvs = C / VEC; if (cvs > NT) return DDPM_E_ARG; int ppi = NT / cvs; \
         dim3 grid(blocks_per_image(x->N, HW, ppi * 4), x->N); \
-        gn_bwd_reduce_kernel<T, VEC><<<grid, NT, sizeof(float) * 4 * C, st>>>(v, d, groups, stats, gamma, beta, eps, act, p_drop, rng, layer_id, ws); \
+        gn_bwd_reduce_kernel<T, VEC><<<grid, NT, sizeof(float) * 6 * C, st>>>(v, d, groups, stats, gamma, beta, eps, act, p_drop, rng, layer_id, ws); \
         LAUNCH_OK(); \
-        gn_bwd_apply_kernel<T, VEC><<<grid, NT, sizeof(float) * (2 * C + 2 * groups), st>>>(v, d, o, groups, stats, gamma, beta, eps, act, p_drop, rng, layer_id, ws, accumulate); \
+        gn_bwd_apply_kernel<T, VEC><<<grid, NT, sizeof(float) * (6 * C + 2 * groups), st>>>(v, d, o, groups, stats, gamma, beta, eps, act, p_drop, rng, layer_id, ws, accumulate); \
         LAUNCH_OK(); }
     if (dtype == DDPM_BF16) { if (vec_ok(x, 8, 2) && vec_ok(dy, 8, 2) && vec_ok(dx, 8, 2)) GO(bf16, 8) else GO(bf16, 1) }
     else if (dtype == DDPM_F32) { if (vec_ok(x, 4, 4) && vec_ok(dy, 4, 4) && vec_ok(dx, 4, 4)) GO(float, 4) else GO(float, 1) }
@@ -396,6 +397,31 @@ extern "C" int ddpm_upsample2x_bwd(const ddpm_tensor* dy, const ddpm_tensor* dx,
         pix_kernel<T, VEC><<<pix_grid(tot), NT, 0, st>>>(dx->N, dx->H, dx->W, dx->C, f); }
     if (dtype == DDPM_BF16) { if (vec_ok(dy, 8, 2) && vec_ok(dx, 8, 2)) GO(bf16, 8) else GO(bf16, 1) }
     else if (dtype == DDPM_F32) { if (vec_ok(dy, 4, 4) && vec_ok(dx, 4, 4)) GO(float, 4) else GO(float, 1) }
+    else return DDPM_E_ARG;
+#undef GO
+    LAUNCH_OK();
+    return 0;
+}
+
+template <typename T, int VEC> struct ZeroUp {
+    TV in, out;
+    __device__ void operator()(int n, int y, int x, int c) const {
+        float v[VEC];
+        if (((y | x) & 1) == 0) ldv<T, VEC>(in.at<T>(n, y >> 1, x >> 1, c), v);
+        else {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) v[i] = 0.f;
+        }
+        stv<T, VEC>(out.at<T>(n, y, x, c), v);
+    }
+};
+extern "C" int ddpm_zero_upsample2x(const ddpm_tensor* x, const ddpm_tensor* out, int dtype, void* stream) {
+    if (!tensor_ok(x) || !tensor_ok(out) || out->H != 2 * x->H || out->W != 2 * x->W || out->C != x->C || out->N != x->N) return DDPM_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+#define GO(T, VEC) { ZeroUp<T, VEC> f{TV(*x), TV(*out)}; int64_t tot = (int64_t)out->N * out->H * out->W * (out->C / VEC); \
+        pix_kernel<T, VEC><<<pix_grid(tot), NT, 0, st>>>(out->N, out->H, out->W, out->C, f); }
+    if (dtype == DDPM_BF16) { if (vec_ok(x, 8, 2) && vec_ok(out, 8, 2)) GO(bf16, 8) else GO(bf16, 1) }
+    else if (dtype == DDPM_F32) { if (vec_ok(x, 4, 4) && vec_ok(out, 4, 4)) GO(float, 4) else GO(float, 1) }
     else return DDPM_E_ARG;
 #undef GO
     LAUNCH_OK();

@@ -203,28 +203,30 @@ extern "C" int ddpm_rng_advance(uint64_t* rng, void* stream) {
 }
 
 // ------------------------------------------------------------------------------------ weight packing
-// OIHW fp32 -> fwd [Cout][tap][Cin] and dgrad [Cin][KH*KW-1-tap][Cout] in the activation dtype.
+// OIHW fp32 -> fwd [CoP][tap][CiP] and dgrad [CiP][KH*KW-1-tap][CoP] in the activation dtype (zero padded).
 template <typename T>
-__global__ void pack_kernel(const float* __restrict__ w, int Cout, int Cin, int KH, int KW, T* wf, T* wd) {
+__global__ void pack_kernel(const float* __restrict__ w, int Cout, int Cin, int KH, int KW, int CiP, int CoP, T* wf, T* wd) {
     const int taps = KH * KW;
-    const int64_t total = (int64_t)Cout * Cin * taps;
+    const int64_t total = (int64_t)CoP * CiP * taps;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         // i enumerates the fwd layout (coalesced writes): co, tap, ci
-        int ci = (int)(i % Cin); int64_t r = i / Cin;
+        int ci = (int)(i % CiP); int64_t r = i / CiP;
         int tap = (int)(r % taps); int co = (int)(r / taps);
-        float v = w[((int64_t)co * Cin + ci) * taps + tap];
+        float v = (ci < Cin && co < Cout) ? w[((int64_t)co * Cin + ci) * taps + tap] : 0.f;
         if (wf) stf<T>(wf + i, v);
-        if (wd) stf<T>(wd + ((int64_t)ci * taps + (taps - 1 - tap)) * Cout + co, v);
+        if (wd) stf<T>(wd + ((int64_t)ci * taps + (taps - 1 - tap)) * CoP + co, v);
     }
 }
 extern "C" int ddpm_pack_weights(const float* w, int Cout, int Cin, int KH, int KW, void* w_fwd, void* w_dgrad,
-                                 int dtype, void* stream) {
+                                 int dtype, int cin_pad, int cout_pad, void* stream) {
     if (!w || (!w_fwd && !w_dgrad) || Cout <= 0 || Cin <= 0 || KH <= 0 || KW <= 0) return DDPM_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    int64_t total = (int64_t)Cout * Cin * KH * KW;
+    int CiP = cin_pad > 0 ? cin_pad : Cin, CoP = cout_pad > 0 ? cout_pad : Cout;
+    if (CiP < Cin || CoP < Cout) return DDPM_E_ARG;
+    int64_t total = (int64_t)CoP * CiP * KH * KW;
     int grid = (int)((total + 255) / 256); if (grid > 148 * 8) grid = 148 * 8;
-    if (dtype == DDPM_F32) pack_kernel<float><<<grid, 256, 0, st>>>(w, Cout, Cin, KH, KW, (float*)w_fwd, (float*)w_dgrad);
-    else if (dtype == DDPM_BF16) pack_kernel<bf16><<<grid, 256, 0, st>>>(w, Cout, Cin, KH, KW, (bf16*)w_fwd, (bf16*)w_dgrad);
+    if (dtype == DDPM_F32) pack_kernel<float><<<grid, 256, 0, st>>>(w, Cout, Cin, KH, KW, CiP, CoP, (float*)w_fwd, (float*)w_dgrad);
+    else if (dtype == DDPM_BF16) pack_kernel<bf16><<<grid, 256, 0, st>>>(w, Cout, Cin, KH, KW, CiP, CoP, (bf16*)w_fwd, (bf16*)w_dgrad);
     else return DDPM_E_ARG;
     LAUNCH_OK();
     return 0;

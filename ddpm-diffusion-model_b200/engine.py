@@ -136,8 +136,8 @@ class WeightCache:
     def bump(self):
         self.epoch += 1
 
-    def get(self, E: "Exec", w: torch.Tensor, dt: int, need_dgrad: bool):
-        key = (id(w), dt)
+    def get(self, E: "Exec", w: torch.Tensor, dt: int, need_dgrad: bool, cin_pad: int = 0, cout_pad: int = 0):
+        key = (id(w), dt, cin_pad, cout_pad)
         ent = self.entries.get(key)
         if ent is not None and ent[4]() is not w:          # id() reused by a new parameter object
             ent = None
@@ -150,20 +150,22 @@ class WeightCache:
         co, ci = w.shape[0], w.shape[1]
         kh, kw = (w.shape[2], w.shape[3]) if w.dim() == 4 else (1, 1)
         tdt = _TORCH[dt]
-        fwd = ent[1] if ent is not None and ent[1] is not None else torch.empty(co * ci * kh * kw, dtype=tdt, device=w.device)
+        n_el = max(co, cout_pad) * max(ci, cin_pad) * kh * kw
+        fwd = ent[1] if ent is not None and ent[1] is not None else torch.empty(n_el, dtype=tdt, device=w.device)
         dg = None
         if need_dgrad:
-            dg = ent[2] if ent is not None and ent[2] is not None else torch.empty(co * ci * kh * kw, dtype=tdt, device=w.device)
+            dg = ent[2] if ent is not None and ent[2] is not None else torch.empty(n_el, dtype=tdt, device=w.device)
         wd = w.detach()
         if not wd.is_contiguous():
             wd = wd.contiguous()
         _lib.call("ddpm_pack_weights", wd.data_ptr(), co, ci, kh, kw, fwd.data_ptr(),
-                  dg.data_ptr() if dg is not None else None, dt, E.stream)
+                  dg.data_ptr() if dg is not None else None, dt, cin_pad, cout_pad, E.stream)
         self.entries[key] = (stamp, fwd, dg, wd, weakref.ref(w))
         return fwd, dg
 
 
 GLOBAL_WCACHE = WeightCache()
+_WORKSPACES: Dict[str, torch.Tensor] = {}
 
 
 class Exec:
@@ -179,6 +181,7 @@ class Exec:
         self.wcache = wcache if wcache is not None else GLOBAL_WCACHE
         self.rng = rng
         self.prefer_tc = 1 if prefer_tc else 0
+        self.use_tc = bool(prefer_tc) and dt == _lib.BF16     # tcgen05 kernels (channel padding to 16)
         self.stream = torch.cuda.current_stream(device).cuda_stream
 
     # ---- allocation helpers
@@ -187,6 +190,15 @@ class Exec:
 
     def f32(self, *shape) -> torch.Tensor:
         return torch.empty(shape, dtype=torch.float32, device=self.device)
+
+    def workspace(self, nbytes: int) -> torch.Tensor:
+        """Scratch for split-K partials; one growing buffer per device (stream-ordered reuse)."""
+        key = str(self.device)
+        ws = _WORKSPACES.get(key)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(max(nbytes, 32 << 20), dtype=torch.uint8, device=self.device)
+            _WORKSPACES[key] = ws
+        return ws
 
     def vec(self, t: torch.Tensor, B: int, Cn: int) -> Act:
         """fp32 [B][C] tensor as an H=W=1 activation (time path)."""
@@ -219,6 +231,7 @@ def conv(E: Exec, x: Act, wpack: torch.Tensor, out: Act, k: int, stride: int = 1
     a.inp, a.out = x.desc(), out.desc()
     a.w = wpack.data_ptr()
     a.bias = bias.data_ptr() if bias is not None else None
+    a.bias_n = bias.numel() if bias is not None else 0
     if tbias is not None:
         a.tbias, a.tbias_pitch = tbias.data_ptr(), tbias.stride(0)
     else:
@@ -237,6 +250,7 @@ def conv(E: Exec, x: Act, wpack: torch.Tensor, out: Act, k: int, stride: int = 1
 
 def wgrad(E: Exec, act: Act, dy: Act, w: torch.nn.Parameter, k: int, stride: int = 1, pad: int = 0,
           a_silu: bool = False) -> None:
+    """dW += dY^T (*) act.  `act` / `dy` may carry zero-padded channels beyond the parameter's shape."""
     g = grad_of(w)
     if g is None:
         return
@@ -248,6 +262,14 @@ def wgrad(E: Exec, act: Act, dy: Act, w: torch.nn.Parameter, k: int, stride: int
     a.a_silu = 1 if a_silu else 0
     a.dtype = act.dt
     a.prefer_tc = E.prefer_tc
+    a.workspace, a.workspace_bytes = None, 0
+    a.cin_valid = w.shape[1] if act.C != w.shape[1] else 0
+    a.cout_valid = w.shape[0] if dy.C != w.shape[0] else 0
+    if E.use_tc and act.dt == _lib.BF16 and stride == 1:
+        need = int(_lib.lib.ddpm_wgrad_workspace_bytes(C.byref(a)))
+        if need > 0:
+            ws = E.workspace(need)
+            a.workspace, a.workspace_bytes = ws.data_ptr(), need
     _lib.call("ddpm_conv_wgrad", C.byref(a), E.stream)
 
 
@@ -289,16 +311,17 @@ def add(E: Exec, a: Act, b: Act, out: Act) -> Act:
     return out
 
 
-def to_nhwc(E: Exec, x: torch.Tensor, halo=1) -> Act:
-    """NCHW-shaped torch tensor (any strides, fp32/bf16) -> pooled NHWC activation."""
+def to_nhwc(E: Exec, x: torch.Tensor, halo=1, cpad: int = 0) -> Act:
+    """NCHW-shaped torch tensor (any strides, fp32/bf16) -> pooled NHWC activation (optionally with the
+    channel count padded with zeros to `cpad` for the tensor-core kernels)."""
     B, Cc, H, W = x.shape
     src_dt = _lib.F32 if x.dtype == torch.float32 else _lib.BF16
     if x.dtype not in (torch.float32, torch.bfloat16):
         x = x.float()
         src_dt = _lib.F32
-    out = E.act(B, H, W, Cc, halo)
+    out = E.act(B, H, W, max(Cc, cpad), halo)
     sn, sc, sh, sw = x.stride()
-    _lib.call("ddpm_nchw_to_nhwc", x.data_ptr(), src_dt, sn, sc, sh, sw, C.byref(out.desc()), E.dt, E.stream)
+    _lib.call("ddpm_nchw_to_nhwc", x.data_ptr(), src_dt, Cc, sn, sc, sh, sw, C.byref(out.desc()), E.dt, E.stream)
     return out
 
 
@@ -455,12 +478,19 @@ def down_fwd(E: Exec, mod, x: Act, out: Optional[Act] = None):
 
 def down_bwd(E: Exec, mod, saved, dout: Act, dx: Optional[Act], dx_accum: bool) -> Act:
     x = saved
-    wgrad(E, x, dout, mod.conv.weight, 3, 2, 1)
     colsum(E, dout, None, mod.conv.bias)
     _, wd = E.wcache.get(E, mod.conv.weight, E.dt, True)
     if dx is None:
         dx, dx_accum = E.act(x.N, x.H, x.W, x.C), False
-    conv(E, dout, wd, dx, 3, 2, 1, accum=dx_accum, mode=_lib.CONV_TRANSPOSED)
+    if E.use_tc and x.H % 2 == 0 and x.W % 2 == 0:
+        # stride-2 gradients as stride-1 tensor-core problems on the zero-interleaved dY
+        up = E.act(x.N, x.H, x.W, dout.C)
+        _lib.call("ddpm_zero_upsample2x", C.byref(dout.desc()), C.byref(up.desc()), E.dt, E.stream)
+        wgrad(E, x, up, mod.conv.weight, 3, 1, 1)
+        conv(E, up, wd, dx, 3, 1, 1, accum=dx_accum)
+    else:
+        wgrad(E, x, dout, mod.conv.weight, 3, 2, 1)
+        conv(E, dout, wd, dx, 3, 2, 1, accum=dx_accum, mode=_lib.CONV_TRANSPOSED)
     return dx
 
 
@@ -570,8 +600,9 @@ def unet_forward(E: Exec, model, x: torch.Tensor, t: torch.Tensor, out_dtype: to
     cur_ch_of = [cats[j].C - enc_out_ch[L - 1 - j] for j in range(L)]
 
     # ---- encoder
-    x_in = to_nhwc(E, x)
-    w_in, _ = E.wcache.get(E, model.in_conv.weight, E.dt, False)
+    cpad = 16 if E.use_tc else 0                       # tcgen05 K-chunk / N granularity
+    x_in = to_nhwc(E, x, cpad=cpad)
+    w_in, _ = E.wcache.get(E, model.in_conv.weight, E.dt, False, cin_pad=cpad)
     cur = conv(E, x_in, w_in, E.act(B, H, W, model.in_conv.out_channels), 3, 1, 1, bias=model.in_conv.bias)
     if G:
         tape.append(("in", x_in))
@@ -630,9 +661,10 @@ def unet_forward(E: Exec, model, x: torch.Tensor, t: torch.Tensor, out_dtype: to
     # ---- head
     st = gn_stats(E, cur, model.out_norm.num_groups)
     a = gn_apply(E, cur, st, model.out_norm, 1, 0.0, 0)
-    w_out, _ = E.wcache.get(E, model.out_conv.weight, E.dt, G)
-    y = conv(E, a, w_out, E.act(B, H, W, model.out_conv.out_channels), 3, 1, 1, bias=model.out_conv.bias)
-    out = to_nchw(E, y, out_dtype)
+    w_out, _ = E.wcache.get(E, model.out_conv.weight, E.dt, G, cout_pad=cpad)
+    oc = model.out_conv.out_channels
+    y = conv(E, a, w_out, E.act(B, H, W, max(oc, cpad)), 3, 1, 1, bias=model.out_conv.bias)
+    out = to_nchw(E, y.slice(0, oc) if y.C != oc else y, out_dtype)
     saved = None
     if G:
         saved = dict(tape=tape, head=(cur, st, a), temb=temb, mlp=mlp_saved, rbs=rbs, cats_shape=[(c.N, c.H, c.W, c.C) for c in cats],
@@ -655,10 +687,12 @@ def unet_backward(E: Exec, model, saved, dy: torch.Tensor, need_dx: bool, progre
     temb = saved["temb"]
 
     # ---- head
-    dyn = to_nhwc(E, dy)
+    cpad = 16 if E.use_tc else 0
+    oc = model.out_conv.out_channels
+    dyn = to_nhwc(E, dy, cpad=cpad)
     wgrad(E, a, dyn, model.out_conv.weight, 3, 1, 1)
-    colsum(E, dyn, None, model.out_conv.bias)
-    _, wd = E.wcache.get(E, model.out_conv.weight, E.dt, True)
+    colsum(E, dyn.slice(0, oc) if dyn.C != oc else dyn, None, model.out_conv.bias)
+    _, wd = E.wcache.get(E, model.out_conv.weight, E.dt, True, cout_pad=cpad)
     da = conv(E, dyn, wd, E.act(a.N, a.H, a.W, a.C), 3, 1, 1)
     dcur = gn_bwd(E, cur_h, st, model.out_norm, 1, 0.0, 0, da, da, False)
     del da, dyn
@@ -711,9 +745,10 @@ def unet_backward(E: Exec, model, saved, dy: torch.Tensor, need_dx: bool, progre
             wgrad(E, x_in, dcur, model.in_conv.weight, 3, 1, 1)
             colsum(E, dcur, None, model.in_conv.bias)
             if need_dx:
-                _, wdi = E.wcache.get(E, model.in_conv.weight, E.dt, True)
+                _, wdi = E.wcache.get(E, model.in_conv.weight, E.dt, True, cin_pad=cpad)
                 dxa = conv(E, dcur, wdi, E.act(x_in.N, x_in.H, x_in.W, x_in.C), 3, 1, 1)
-                dx = to_nchw(E, dxa, torch.float32)
+                ic = model.in_conv.in_channels
+                dx = to_nchw(E, dxa.slice(0, ic) if dxa.C != ic else dxa, torch.float32)
     # ---- time path (the per-block time_proj gradients were produced inside the loop)
     if dtemb is not None:
         time_mlp_bwd(E, model.time_mlp, saved["mlp"], dtemb)

@@ -79,7 +79,9 @@ int ddpm_ddim_step(void* sched, const float* xt, const void* eps, int eps_dtype,
 int ddpm_to_image01(const float* x, float* out, int64_t n, void* stream);
 
 /* ---------------- layout at the API boundary (NCHW-shaped, any strides <-> NHWC) ---------- */
-int ddpm_nchw_to_nhwc(const void* src, int src_dtype, int64_t sn, int64_t sc, int64_t sh,
+/* dst->C may exceed src_C (channel padding for the tensor-core kernels): the extra channels are
+ * written as zeros. */
+int ddpm_nchw_to_nhwc(const void* src, int src_dtype, int src_C, int64_t sn, int64_t sc, int64_t sh,
                       int64_t sw, const ddpm_tensor* dst, int dst_dtype, void* stream);
 int ddpm_nhwc_to_nchw(const ddpm_tensor* src, int src_dtype, void* dst, int dst_dtype, int64_t sn,
                       int64_t sc, int64_t sh, int64_t sw, void* stream);
@@ -106,6 +108,9 @@ int ddpm_gn_bwd(const ddpm_tensor* x, int dtype, int groups, const double* stats
 /* nearest x2 (unet_backbone.py:63) and its adjoint (2x2 sum) */
 int ddpm_upsample2x(const ddpm_tensor* x, const ddpm_tensor* out, int dtype, void* stream);
 int ddpm_upsample2x_bwd(const ddpm_tensor* dy, const ddpm_tensor* dx, int dtype, int accumulate, void* stream);
+/* out[n,2y,2x] = x[n,y,x], zeros elsewhere (whole interior written): turns the data / weight gradient
+ * of a stride-2 convolution into stride-1 problems for the tensor-core kernels */
+int ddpm_zero_upsample2x(const ddpm_tensor* x, const ddpm_tensor* out, int dtype, void* stream);
 /* out = a + b (all three may alias channel slices); used for gradient fan-in */
 int ddpm_add(const ddpm_tensor* a, const ddpm_tensor* b, const ddpm_tensor* out, int dtype, void* stream);
 /* out_nc[n][c] = sum_pixels dy (fp32, overwritten, may be NULL); dbias[c] += sum_n (may be NULL) */
@@ -122,7 +127,7 @@ typedef struct {
     ddpm_tensor in;        /* activations (or dY for dgrad) */
     ddpm_tensor out;       /* result view (may be a channel slice of a wider buffer) */
     const void* w;         /* packed weights [Cout][KH*KW][Cin] in `dtype` (see ddpm_pack_weights) */
-    const float* bias;     /* fp32 [Cout] or NULL */
+    const float* bias;     /* fp32 [bias_n] or NULL */
     const float* tbias;    /* per-image bias fp32 [N][tbias_pitch] or NULL (time_proj output; the time path is fp32) */
     int32_t tbias_pitch;
     ddpm_tensor res;       /* residual added in the epilogue; res.ptr == NULL for none */
@@ -133,6 +138,7 @@ typedef struct {
     int32_t epi;           /* DDPM_EPI_* flags */
     int32_t dtype;
     int32_t prefer_tc;     /* 1: use the tcgen05 kernel when the shape qualifies (bf16 only) */
+    int32_t bias_n;        /* entries in `bias` (0: out.C); fewer when out carries zero-padded channels */
 } ddpm_conv_args;
 int ddpm_conv(const ddpm_conv_args* a, void* stream);
 /* test / tuning hooks: force the CUDA-core kernels; choose the tcgen05 operand layout
@@ -148,12 +154,18 @@ typedef struct {
     int32_t a_silu;
     int32_t dtype;
     int32_t prefer_tc;
+    void* workspace;          /* split-K partials for the tensor-core kernel (may be NULL -> CUDA cores) */
+    int64_t workspace_bytes;
+    int32_t cin_valid, cout_valid; /* >0: act / dy carry zero-padded channels; dw is [cout_valid][cin_valid][KH][KW] */
 } ddpm_wgrad_args;
 int ddpm_conv_wgrad(const ddpm_wgrad_args* a, void* stream);
+/* bytes of workspace the tensor-core wgrad wants for this problem (0: it will not be used) */
+int64_t ddpm_wgrad_workspace_bytes(const ddpm_wgrad_args* a);
 
-/* fp32 OIHW -> [Cout][KH*KW][Cin] (fwd) and flipped/transposed [Cin][KH*KW][Cout] (dgrad). */
+/* fp32 OIHW -> [Cout_pad][KH*KW][Cin_pad] (fwd) and flipped/transposed [Cin_pad][KH*KW][Cout_pad]
+ * (dgrad); padded rows/columns are zero.  cin_pad / cout_pad <= 0 mean "no padding". */
 int ddpm_pack_weights(const float* w, int Cout, int Cin, int KH, int KW, void* w_fwd, void* w_dgrad,
-                      int dtype, void* stream);
+                      int dtype, int cin_pad, int cout_pad, void* stream);
 
 /* ---------------- attention: attention.py:56-74 -------------------------------------------- */
 /* qkv: NHWC with channel = s*heads*d + head*d + i (s in q,k,v) -- the layout conv `qkv` emits, so
