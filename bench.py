@@ -231,8 +231,11 @@ def run_ours(args):
         return
     for _ in range(max(3, args.warmup)):
         step_resident()
+    from ddpm_diffusion_model_b200 import engine as _engine
+    miss0 = _engine.POOL.misses
     with ClockSampler(local) as clk:
         sec, launches, last = timed(step_resident, args.steps)
+    pool_misses = _engine.POOL.misses - miss0
     for _ in range(2):
         step_e2e()
     sec_e2e, _, last_e2e = timed(step_e2e, args.steps)
@@ -263,7 +266,7 @@ def run_ours(args):
             "e2e": {"value": e2e, "unit": "img/s", "h2d_bytes_per_step": B * 3 * 64 * 64 * 4, "d2h_bytes_per_step": 4,
                     "ms_per_step": sec_e2e / args.steps * 1e3},
             "gpu_launches": launches, "clocks": clk.summary(), "roofline": roof, "cpu_baseline": cpu,
-            "loss": last[0] if last else None,
+            "loss": last[0] if last else None, "pool_misses_in_timed_region": pool_misses,
             "train_tflops_per_gpu": TRAIN_GF_PER_IMG * 1e9 * B * args.steps / sec / 1e12,
         }
         print(json.dumps(line), flush=True)

@@ -68,6 +68,7 @@ SIGNATURES = {
     "ddpm_sinusoid": [_vp, _i, _i, _i, _vp, _i, _vp],
     "ddpm_gn_stats": [_TP, _i, _i, _vp, _vp],
     "ddpm_gn_apply": [_TP, _i, _i, _vp, _vp, _vp, _f, _i, _f, _vp, _u32, _TP, _vp],
+    "ddpm_gn_fwd": [_TP, _i, _i, _vp, _vp, _vp, _f, _i, _f, _vp, _u32, _TP, _vp],
     "ddpm_gn_bwd": [_TP, _i, _i, _vp, _vp, _vp, _f, _i, _f, _vp, _u32, _TP, _TP, _i, _vp, _vp, _vp, _vp],
     "ddpm_upsample2x": [_TP, _TP, _i, _vp],
     "ddpm_upsample2x_bwd": [_TP, _TP, _i, _i, _vp],
@@ -88,6 +89,7 @@ SIGNATURES = {
     "ddpm_rng_advance": [_vp, _vp],
     "ddpm_set_force_simt": [_i],
     "ddpm_set_tc_mode": [_i, _i],
+    "ddpm_set_tc_v2": [_i],
 }
 
 

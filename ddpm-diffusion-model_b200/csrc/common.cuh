@@ -70,10 +70,11 @@ template <> struct Vec16<bf16> {
     }
 };
 
-__device__ __forceinline__ float silu_f(float z) { return z / (1.0f + __expf(-z)); }
+// SiLU via ex2.approx + rcp.approx (2 MUFU per element; ~2 ulp, far inside the 1e-4 fp32 parity budget)
+__device__ __forceinline__ float silu_f(float z) { return __fdividef(z, 1.0f + __expf(-z)); }
 __device__ __forceinline__ float dsilu_f(float z) {
-    float s = 1.0f / (1.0f + __expf(-z));
-    return s * (1.0f + z * (1.0f - s));
+    float s = __fdividef(1.0f, 1.0f + __expf(-z));
+    return s * fmaf(z, 1.0f - s, 1.0f);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -150,6 +151,25 @@ __device__ __forceinline__ uint32_t dropout_mask(const uint64_t* rng, uint32_t l
         m |= ((r.w >> 8) >= thr ? 1u : 0u) << (4 * q + 3);
     }
     return m;
+}
+// Dropout keep-bits from 16-bit words: ONE Philox call per 8 consecutive elements (e0 % VEC == 0, VEC in
+// {1, 4, 8}); element e uses 16-bit word (e & 7) of the call with counter e >> 3, so the fp32 (VEC 4), bf16
+// (VEC 8) and scalar paths draw the same mask.  keep iff word >= thr16 = round(p * 65536).
+template <int VEC>
+__device__ __forceinline__ uint32_t dropout_mask16(const uint64_t* rng, uint32_t layer, uint64_t e0, uint32_t thr16) {
+    const uint64_t seed = rng[0], step = rng[1];
+    const uint64_t e = e0 >> 3;
+    const uint4 r = philox4((uint32_t)seed, (uint32_t)(seed >> 32),
+                            make_uint4((uint32_t)e, (uint32_t)(e >> 32), (uint32_t)step, layer));
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint32_t h = (w[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
+        m |= (h >= thr16 ? 1u : 0u) << i;
+    }
+    if (VEC == 8) return m;
+    return (m >> (uint32_t)(e0 & 7)) & ((1u << VEC) - 1u);
 }
 // keep-mask for element index `e` (one Philox call covers 4 consecutive elements)
 __device__ __forceinline__ bool dropout_keep(const uint64_t* rng, uint32_t layer, uint64_t e, float p) {

@@ -25,10 +25,12 @@
 #define TC_THREADS 192
 #define KC 16                 // channels per K-chunk (one UMMA K step for bf16)
 
+static int sm_count();
 static int g_tc_mode = 1;     // 0: SWIZZLE_NONE ("interleave") operand layout, 1: SWIZZLE_32B (default)
 static int g_tc_baseoff = 0;  // measured on B200: the swizzle is a pure function of the smem address, so row-shifted
                               // descriptors need base_offset = 0 (setting it from the address gives wrong results)
-extern "C" int ddpm_set_tc_mode(int mode, int baseoff) { g_tc_mode = mode; g_tc_baseoff = baseoff; return 0; }
+static int g_tc_exp = 0;      // diagnostics only (tools/kbench.py): bit0 skip A loads after the first ring fill, bit1 same for B
+extern "C" int ddpm_set_tc_mode(int mode, int baseoff) { g_tc_mode = mode & 1; g_tc_exp = mode >> 4; g_tc_baseoff = baseoff; return 0; }
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -40,6 +42,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
@@ -119,7 +124,7 @@ struct TcParams {
     int a_stage_bytes, b_stage_bytes;
     int tmem_cols;              // power of two >= MT*NT
     int has_res, accum;
-    int baseoff;
+    int baseoff, exp;
     int sub;                    // 1: stride-2 conv = stride-1 conv kept at even (y, x) only
 };
 
@@ -164,9 +169,10 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                 const int sa = kc % p.SA; const uint32_t pa = (kc / p.SA) & 1;
                 mbar_wait(&a_empty[sa], pa ^ 1);
                 uint8_t* adst = a_ring + (size_t)sa * p.a_stage_bytes;
-                mbar_expect_tx(&a_full[sa], (uint32_t)(p.P * 32));
+                const bool skipA = (p.exp & 1) && kc >= p.SA;
+                if (skipA) mbar_arrive(&a_full[sa]); else mbar_expect_tx(&a_full[sa], (uint32_t)(p.P * 32));
                 const int row0 = Q0 - halo_rows;
-                for (int r = 0; r < p.P; r += p.seg) {          // one TMA box of `seg` rows per op
+                for (int r = 0; r < p.P && !skipA; r += p.seg) {          // one TMA box of `seg` rows per op
                     if (SW32) {
                         tma_load_2d(adst + (size_t)r * 32, &tmA, &a_full[sa], kc * KC, row0 + r);
                     } else {
@@ -177,8 +183,9 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                 for (int g = 0; g < BG; ++g) {
                     mbar_wait(&b_empty[sb], pb ^ 1);
                     uint8_t* bdst = b_ring + (size_t)sb * p.b_stage_bytes;
-                    mbar_expect_tx(&b_full[sb], (uint32_t)(p.tpb * p.NT * 32));
-                    for (int t = 0; t < p.tpb; ++t) {
+                    const bool skipB = (p.exp & 2) && (kc * BG + g) >= p.SB;
+                    if (skipB) mbar_arrive(&b_full[sb]); else mbar_expect_tx(&b_full[sb], (uint32_t)(p.tpb * p.NT * 32));
+                    for (int t = 0; t < p.tpb && !skipB; ++t) {
                         const int tap = g * p.tpb + t;
                         if (SW32) tma_load_3d(bdst + (size_t)t * p.NT * 32, &tmB, &b_full[sb], kc * KC, tap, n0);
                         else tma_load_4d(bdst + (size_t)t * p.NT * 32, &tmB, &b_full[sb], 0, n0, kc * 2, tap);
@@ -360,8 +367,11 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams
     return 0;
 }
 
+static int conv_tc2_launch(const ddpm_conv_args* a, cudaStream_t st);
+extern int g_tc_v2_flag();
 int conv_tc_launch(const ddpm_conv_args* a, cudaStream_t st) {
     int rc = get_encode(); if (rc) return rc;
+    if (g_tc_v2_flag() && g_tc_mode == 1 && g_tc_exp == 0) return conv_tc2_launch(a, st);
     const bool sw32 = g_tc_mode == 1;
     TcParams p;
     p.out = TV(a->out);
@@ -373,7 +383,7 @@ int conv_tc_launch(const ddpm_conv_args* a, cudaStream_t st) {
     p.Hp = a->in.H + 2; p.Wp = a->in.W + 2; p.H = a->in.H; p.W = a->in.W;
     p.Qtot = a->in.N * p.Hp * p.Wp;
     p.accum = (a->epi & DDPM_EPI_ACCUM) ? 1 : 0;
-    p.baseoff = g_tc_baseoff;
+    p.baseoff = g_tc_baseoff; p.exp = g_tc_exp;
     p.sub = a->stride == 2 ? 1 : 0;
     int MT = 256 / p.NT; if (MT >= 2) MT = 2; if (MT < 1) MT = 1;
     int halo_rows = p.taps == 9 ? p.Wp + 1 : 0;
@@ -417,6 +427,328 @@ int conv_tc_launch(const ddpm_conv_args* a, cudaStream_t st) {
     dim3 grid(ceil_div(p.Qtot, 128 * MT), p.Cout / p.NT);
     if (MT == 2) return sw32 ? launch<2, true>(tmA, tmB, p, grid, smem, st) : launch<2, false>(tmA, tmB, p, grid, smem, st);
     return sw32 ? launch<1, true>(tmA, tmB, p, grid, smem, st) : launch<1, false>(tmA, tmB, p, grid, smem, st);
+}
+
+// ================================================================================================
+// v2: persistent CTA-PAIR kernel (cta_group::2), TMEM double-buffered
+//
+// Why (ncu, profiles/r1_conv_tc_v1_192x192_64.txt): v1 re-fetches the whole 9-tap weight slab for every
+// 128/256-pixel tile -- 87 % of its 3.3 GB of L2->SM traffic at 192->192@64 -- and two co-resident CTAs
+// fall into lock-step, so the tensor pipe is active 33 % of the time.  Here
+//   * two CTAs of a cluster (one TPC) issue M=256 MMAs: each CTA stages its own 128*MT pixel rows (A) but
+//     only HALF of the weight tile (B); the tensor cores of both SMs read both halves -> B traffic / 2;
+//   * one CTA per SM, ~200 KB operand ring (6-8 K-chunks in flight, covers the TMA round trip);
+//   * the CTA pair is persistent and walks (pixel tile, channel tile) items; accumulators are double
+//     buffered in TMEM (2 x MT*NT columns), so the epilogue of item i overlaps the MMAs of item i+1 and
+//     the producer prefetches across item boundaries.
+// Barrier protocol (same smem offsets in both CTAs):
+//   full[s]   (leader)  : 1 arrive.expect_tx(bytes of BOTH CTAs); both CTAs' TMA loads complete_tx on it
+//   empty[s]  (each CTA): tcgen05.commit.cta_group::2 multicast to both CTAs
+//   tfull[b]  (each CTA): commit multicast after the item's last MMA -> the CTA's own epilogue warps
+//   tempty[b] (leader)  : 4 epilogue warps x 2 CTAs arrive (remote arrive from the peer)
+// ================================================================================================
+#define TC2_THREADS 192
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(m), "r"(bar_cluster_addr), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma2_load_3d(void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(m), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {      // arrives on `bar` in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
+struct Tc2Params {
+    TV out, res;
+    const float* bias; const float* tbias; int tbias_pitch; int bias_n;
+    int Cin, Cout, NT, n_tiles;   // NT: UMMA N (full tile, both halves); each CTA stages NT/2 weight rows per tap
+    int taps;                     // 9 or 1
+    int Hp, Wp, H, W, Qtot;
+    int P, seg;                   // patch rows per K-chunk, TMA box height
+    int KS;                       // K-chunks per ring stage (1 for 3x3, up to 4 for 1x1)
+    int S;                        // ring depth
+    int a_chunk_bytes, b_chunk_bytes, stage_bytes;
+    int pix_tiles, items;
+    int has_res, accum, sub;
+};
+
+template <int MT>
+__global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                    const __grid_constant__ CUtensorMap tmB, Tc2Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* ring = smem;
+    uint64_t* bars = (uint64_t*)(ring + (size_t)p.S * p.stage_bytes);
+    uint64_t* full = bars;            uint64_t* empty = full + p.S;
+    uint64_t* tfull = empty + p.S;    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int KCH = p.Cin / KC;
+    const int NST = (KCH + p.KS - 1) / p.KS;            // ring stages per item
+    const int halo_rows = (p.taps == 9) ? p.Wp + 1 : 0;
+    const int tile_rows = 128 * MT;
+    const int cols_per_buf = MT * p.NT;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < p.S; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 8); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc2(tmem_slot, 512u);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                  // peer's barriers are initialised before anyone signals them
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================================================================== TMA producer (both CTAs)
+        if (lane == 0) {
+            uint32_t g = 0;                              // global stage counter (continues across items)
+            for (int it = pair; it < p.items; it += npairs) {
+                const int pt = it / p.n_tiles, ntile = it - pt * p.n_tiles;
+                const int Q0 = pt * (2 * tile_rows) + (int)rank * tile_rows;
+                const int nrow0 = ntile * p.NT + (int)rank * (p.NT / 2);
+                for (int st = 0; st < NST; ++st, ++g) {
+                    const int s = g % p.S; const uint32_t ph = (g / p.S) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    const int kc0 = st * p.KS, nk = min(p.KS, KCH - kc0);
+                    const uint32_t fbar = mapa_u32(smem_u32(&full[s]), 0);
+                    if (leader) mbar_expect_tx(&full[s], (uint32_t)(2 * nk * (p.P * 32 + p.b_chunk_bytes)));
+                    uint8_t* sbase = ring + (size_t)s * p.stage_bytes;
+                    for (int k = 0; k < nk; ++k) {
+                        uint8_t* adst = sbase + (size_t)k * (p.a_chunk_bytes + p.b_chunk_bytes);
+                        uint8_t* bdst = adst + p.a_chunk_bytes;
+                        const int row0 = Q0 - halo_rows;
+                        for (int r = 0; r < p.P; r += p.seg)
+                            tma2_load_2d(adst + (size_t)r * 32, &tmA, fbar, (kc0 + k) * KC, row0 + r);
+                        tma2_load_3d(bdst, &tmB, fbar, (kc0 + k) * KC, nrow0, 0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================================== MMA issuer (leader CTA only)
+        if (leader && lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((256u >> 4) << 24);
+            uint32_t g = 0, j = 0;
+            for (int it = pair; it < p.items; it += npairs, ++j) {
+                const uint32_t buf = j & 1, bph = (j >> 1) & 1;
+                mbar_wait(&tempty[buf], bph ^ 1);        // both CTAs' epilogues have drained this accumulator buffer
+                tc_fence_after();
+                const uint32_t dbase = tmem_base + buf * (uint32_t)cols_per_buf;
+                for (int st = 0; st < NST; ++st, ++g) {
+                    const int s = g % p.S; const uint32_t ph = (g / p.S) & 1;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const int kc0 = st * p.KS, nk = min(p.KS, KCH - kc0);
+                    const uint32_t sbase = smem_u32(ring + (size_t)s * p.stage_bytes);
+                    for (int k = 0; k < nk; ++k) {
+                        const uint32_t a_base = sbase + (uint32_t)(k * (p.a_chunk_bytes + p.b_chunk_bytes));
+                        const uint32_t b_base = a_base + (uint32_t)p.a_chunk_bytes;
+                        for (int tap = 0; tap < p.taps; ++tap) {
+                            const int shift = (p.taps == 9) ? (tap / 3) * p.Wp + (tap % 3) : 0;
+                            const uint64_t bdesc = make_desc(b_base + (uint32_t)(tap * (p.NT / 2) * 32), 16u, 256u, 6u, 0);
+#pragma unroll
+                            for (int mt = 0; mt < MT; ++mt) {
+                                const uint64_t adesc = make_desc(a_base + (uint32_t)((mt * 128 + shift) * 32), 16u, 256u, 6u, 0);
+                                umma2_bf16(dbase + (uint32_t)(mt * p.NT), adesc, bdesc, idesc, (st | k | tap) != 0 ? 1u : 0u);
+                            }
+                        }
+                    }
+                    umma2_commit_mc(&empty[s]);
+                }
+                umma2_commit_mc(&tfull[buf]);
+            }
+        }
+    } else {
+        // ===================================================================== epilogue (both CTAs)
+        const int qd = warp & 3;
+        const int HpWp = p.Hp * p.Wp;
+        const uint32_t tempty_leader0 = mapa_u32(smem_u32(&tempty[0]), 0);
+        const uint32_t tempty_leader1 = mapa_u32(smem_u32(&tempty[1]), 0);
+        uint32_t j = 0;
+        for (int it = pair; it < p.items; it += npairs, ++j) {
+            const uint32_t buf = j & 1, bph = (j >> 1) & 1;
+            const int pt = it / p.n_tiles, ntile = it - pt * p.n_tiles;
+            const int Q0 = pt * (2 * tile_rows) + (int)rank * tile_rows;
+            const int n0 = ntile * p.NT;
+            mbar_wait(&tfull[buf], bph);
+            tc_fence_after();
+            const uint32_t dbase = tmem_base + buf * (uint32_t)cols_per_buf;
+#pragma unroll 1
+            for (int mt = 0; mt < MT; ++mt) {
+                const int Q = Q0 + mt * 128 + qd * 32 + lane;
+                bool valid = Q < p.Qtot;
+                int n = 0, y = 0, x = 0;
+                if (valid) {
+                    n = Q / HpWp; int r = Q - n * HpWp; int yp = r / p.Wp; int xp = r - yp * p.Wp;
+                    y = yp - 1; x = xp - 1;
+                    valid = y >= 0 && y < p.H && x >= 0 && x < p.W;
+                    if (p.sub) { valid = valid && ((y | x) & 1) == 0; y >>= 1; x >>= 1; }
+                }
+                bf16* orow = valid ? p.out.at<bf16>(n, y, x, n0) : nullptr;
+                const bf16* rrow = (valid && p.has_res) ? p.res.at<bf16>(n, y, x, n0) : nullptr;
+                const float* tb = (valid && p.tbias) ? p.tbias + (size_t)n * p.tbias_pitch + n0 : nullptr;
+#pragma unroll 1
+                for (int c0 = 0; c0 < p.NT; c0 += 16) {
+                    uint32_t r[16];
+                    tmem_ld16(dbase + ((uint32_t)(qd * 32) << 16) + (uint32_t)(mt * p.NT + c0), r);
+                    tmem_ld_wait();
+                    if (valid && n0 + c0 < p.Cout) {
+                        float v[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+                        if (p.bias) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) if (n0 + c0 + i < p.bias_n) v[i] += __ldg(p.bias + n0 + c0 + i);
+                        }
+                        if (tb) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[i] += __ldg(tb + c0 + i);
+                        }
+                        if (rrow) {
+                            uint4 a = *reinterpret_cast<const uint4*>(rrow + c0), b = *reinterpret_cast<const uint4*>(rrow + c0 + 8);
+                            const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
+                            const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&b);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                float2 fa = __bfloat1622float2(ha[i]), fb = __bfloat1622float2(hb[i]);
+                                v[2 * i] += fa.x; v[2 * i + 1] += fa.y; v[8 + 2 * i] += fb.x; v[8 + 2 * i + 1] += fb.y;
+                            }
+                        }
+                        if (p.accum) {
+                            uint4 a = *reinterpret_cast<const uint4*>(orow + c0), b = *reinterpret_cast<const uint4*>(orow + c0 + 8);
+                            const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
+                            const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&b);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                float2 fa = __bfloat1622float2(ha[i]), fb = __bfloat1622float2(hb[i]);
+                                v[2 * i] += fa.x; v[2 * i + 1] += fa.y; v[8 + 2 * i] += fb.x; v[8 + 2 * i + 1] += fb.y;
+                            }
+                        }
+                        uint4 o0, o1;
+                        __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&o0);
+                        __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&o1);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            h0[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                            h1[i] = __floats2bfloat162_rn(v[8 + 2 * i], v[8 + 2 * i + 1]);
+                        }
+                        *reinterpret_cast<uint4*>(orow + c0) = o0;
+                        *reinterpret_cast<uint4*>(orow + c0 + 8) = o1;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(buf ? tempty_leader1 : tempty_leader0);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                  // nobody exits (or frees TMEM) while the pair is still working
+    if (warp == 1) { tc_fence_after(); tmem_dealloc2(tmem_base, 512u); }
+}
+
+static int g_tc_v2 = 1;
+extern "C" int ddpm_set_tc_v2(int on) { g_tc_v2 = on; return 0; }
+int g_tc_v2_flag() { return g_tc_v2; }
+
+static int conv_tc2_launch(const ddpm_conv_args* a, cudaStream_t st) {
+    Tc2Params p;
+    p.out = TV(a->out);
+    p.has_res = a->res.ptr != nullptr; p.res = p.has_res ? TV(a->res) : TV(a->out);
+    p.bias = a->bias; p.tbias = a->tbias; p.tbias_pitch = a->tbias_pitch;
+    p.bias_n = a->bias_n > 0 ? a->bias_n : a->out.C;
+    p.Cin = a->in.C; p.Cout = a->out.C; p.NT = pick_nt(p.Cout); p.n_tiles = p.Cout / p.NT;
+    p.taps = a->KH * a->KW;
+    p.Hp = a->in.H + 2; p.Wp = a->in.W + 2; p.H = a->in.H; p.W = a->in.W;
+    p.Qtot = a->in.N * p.Hp * p.Wp;
+    p.accum = (a->epi & DDPM_EPI_ACCUM) ? 1 : 0;
+    p.sub = a->stride == 2 ? 1 : 0;
+    int MT = 256 / p.NT; if (MT > 2) MT = 2; if (MT < 1) MT = 1;
+    // small problems: prefer more, smaller items so that every SM pair gets one
+    if (MT == 2 && (int64_t)ceil_div(p.Qtot, 512) * p.n_tiles < sm_count() / 2) MT = 1;
+    const int halo_rows = p.taps == 9 ? p.Wp + 1 : 0;
+    {
+        int need = 128 * MT + 2 * halo_rows;
+        int nseg = (need + 255) / 256;
+        p.seg = (((need + nseg - 1) / nseg) + 7) & ~7;
+        p.P = p.seg * nseg;
+    }
+    p.a_chunk_bytes = (p.P * 32 + 255) & ~255;
+    p.b_chunk_bytes = p.taps * (p.NT / 2) * 32;             // multiple of 256: NT/2 is a multiple of 8
+    const int KCH = p.Cin / KC;
+    p.KS = p.taps == 9 ? 1 : (KCH < 4 ? KCH : 4);
+    p.stage_bytes = (p.KS * (p.a_chunk_bytes + p.b_chunk_bytes) + 1023) & ~1023;
+    const int budget = 212 * 1024;
+    p.S = budget / p.stage_bytes; if (p.S > 12) p.S = 12;
+    if (p.S < 2) return DDPM_E_ARG;
+    p.pix_tiles = ceil_div(p.Qtot, 256 * MT);
+    p.items = p.pix_tiles * p.n_tiles;
+    size_t smem = (size_t)p.S * p.stage_bytes + 8 * (2 * p.S + 4) + 16 + 1024;
+
+    CUtensorMap tmA, tmB;
+    {
+        uint64_t da[2] = {(uint64_t)p.Cin, (uint64_t)p.Qtot}; uint64_t sa[1] = {(uint64_t)a->in.pitch * 2};
+        uint32_t ba[2] = {KC, (uint32_t)p.seg};
+        if (encode(&tmA, a->in.ptr, 2, da, sa, ba, CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
+        // weights [Cout][taps][Cin] viewed as (c, n, tap): one box brings all taps of NT/2 rows -> smem [tap][n][16 ch]
+        uint64_t db[3] = {(uint64_t)p.Cin, (uint64_t)p.Cout, (uint64_t)p.taps};
+        uint64_t sb[2] = {(uint64_t)p.taps * p.Cin * 2, (uint64_t)p.Cin * 2};
+        uint32_t bb[3] = {KC, (uint32_t)(p.NT / 2), (uint32_t)p.taps};
+        if (encode(&tmB, (void*)a->w, 3, db, sb, bb, CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
+    }
+    int pairs = sm_count() / 2; if (pairs > p.items) pairs = p.items; if (pairs < 1) pairs = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(TC2_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    static size_t configured[3] = {0, 0, 0};
+    if (MT == 2) {
+        if (smem > configured[2]) { CUDA_TRY(cudaFuncSetAttribute(conv_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured[2] = smem; }
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<2>, tmA, tmB, p));
+    } else {
+        if (smem > configured[1]) { CUDA_TRY(cudaFuncSetAttribute(conv_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured[1] = smem; }
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<1>, tmA, tmB, p));
+    }
+    LAUNCH_OK();
+    return 0;
 }
 
 // ================================================================================================
@@ -555,6 +887,15 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restr
     }
 }
 
+static int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
 static int wg_pick_nt(int Cin) {
     for (int nt = 128; nt >= 16; nt -= 16) if (Cin % nt == 0) return nt;
     return 0;
@@ -571,7 +912,9 @@ static void wg_plan(const ddpm_wgrad_args* a, WgTcParams* p, int* splits) {
     p->stage_bytes = 2 * WG_KQ * 128 + p->nblkA * WG_ROWS * 128;
     p->tmem_cols = 32; while (p->tmem_cols < p->ntap * p->NT) p->tmem_cols <<= 1;
     int yz = p->ntap * p->n_tiles * p->m_tiles;
-    int sp = (148 + yz - 1) / yz;
+    // one CTA per SM (176 KB of shared memory): the grid must not exceed ONE wave, or the second,
+    // nearly empty wave doubles the kernel's duration -> floor, not ceil
+    int sp = sm_count() / yz;
     int max_sp = (p->stages_total + 7) / 8; if (max_sp < 1) max_sp = 1;
     if (sp > max_sp) sp = max_sp;
     if (sp < 1) sp = 1;

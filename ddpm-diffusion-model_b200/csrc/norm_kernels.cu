@@ -10,6 +10,9 @@
 // HBM roofline (bf16 activations): gn_stats 2 B/elem, gn_apply 4 B/elem, gn_bwd 2x(4)+2 = 10 B/elem.
 #include "common.cuh"
 
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
 #define NT 256
 
 struct PixMap {
@@ -42,6 +45,23 @@ template <typename T, int VEC> __device__ __forceinline__ void stv(T* p, const f
         for (int i = 0; i < VEC; ++i) t.v[i] = v[i];
         t.store(p); }
 }
+// raw 16-byte (or scalar) packet: loads are issued back to back and converted later, so a thread keeps
+// U independent requests in flight at 4 registers each
+template <typename T, int VEC> struct Raw { uint4 q; };
+template <typename T> struct Raw<T, 1> { T q; };
+template <typename T, int VEC> __device__ __forceinline__ void ldraw(const T* p, Raw<T, VEC>& r) {
+    if constexpr (VEC == 1) r.q = *p; else r.q = *reinterpret_cast<const uint4*>(p);
+}
+template <typename T, int VEC> __device__ __forceinline__ void unraw(const Raw<T, VEC>& r, float* v) {
+    if constexpr (VEC == 1) { v[0] = ldf<T>(&r.q); }
+    else if constexpr (sizeof(T) == 4) {
+        v[0] = __uint_as_float(r.q.x); v[1] = __uint_as_float(r.q.y); v[2] = __uint_as_float(r.q.z); v[3] = __uint_as_float(r.q.w);
+    } else {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r.q);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+    }
+}
 
 static inline bool vec_ok(const ddpm_tensor* t, int vec, int esz) {
     return (t->C % vec) == 0 && (t->pitch % vec) == 0 && ((((uintptr_t)t->ptr) % (vec * esz)) == 0);
@@ -53,118 +73,369 @@ static inline int blocks_per_image(int N, int HW, int ppi) {
     return want < maxb ? want : maxb;
 }
 
-// ------------------------------------------------------------------------------------ gn_stats
-template <typename T, int VEC>
-__global__ void __launch_bounds__(NT, 4) gn_stats_kernel(TV x, int G, double* stats) {
-    extern __shared__ double sg[];          // [G][2]
-    const int n = blockIdx.y, cpg = x.C / G;
-    for (int i = threadIdx.x; i < 2 * G; i += NT) sg[i] = 0.0;
-    __syncthreads();
-    PixMap m = make_map<VEC>(x.C);
-    if (m.cvs > NT) {                        // very wide tensors: loop channel vectors too
-        // (not reachable for C <= 2048 with VEC >= 4; scalar path handles C <= 256)
-    }
-    float s[VEC], q[VEC];
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) { s[i] = 0.f; q[i] = 0.f; }
-    const int HW = x.H * x.W;
-    const int per = (HW + gridDim.x - 1) / gridDim.x;
-    const int p0 = blockIdx.x * per, p1 = min(HW, p0 + per);
-    if (m.active) {
-        for (int p = p0 + m.prow; p < p1; p += m.ppi) {
-            int y = p / x.W, xx = p - y * x.W;
-            float v[VEC];
-            ldv<T, VEC>(x.at<T>(n, y, xx, m.cv * VEC), v);
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) { s[i] += v[i]; q[i] += v[i] * v[i]; }
-        }
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-            int g = (m.cv * VEC + i) / cpg;
-            atomicAdd(&sg[2 * g], (double)s[i]);
-            atomicAdd(&sg[2 * g + 1], (double)q[i]);
-        }
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 2 * G; i += NT) atomicAdd(&stats[(size_t)n * 2 * G + i], sg[i]);
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+// ================================================================================================
+// GroupNorm, one thread-block CLUSTER per image.
+//
+// The reference's chain cast -> native_group_norm(fp32) -> SiLU -> dropout -> cast moves 20-37 B per
+// element.  Here an image is owned by a cluster of CS CTAs:
+//   phase 1  every CTA streams its share of the image's pixels from HBM and reduces per-channel
+//            moments (registers -> shared memory), the CTAs exchange per-group (forward) or
+//            per-channel (backward) partials through distributed shared memory,
+//   phase 2  the same CTA re-reads the same pixels -- now L2 hits, the image was touched microseconds
+//            ago and at most ~50 clusters are in flight -- and writes the result.
+// HBM traffic: forward 2 (read) + 2 (write) = 4 B/elem bf16, backward 4 + 2 = 6 B/elem (+2 when
+// accumulating into dx), instead of 6 and 10 for separate stats / apply launches.
+// Thread mapping: a thread owns one 16-byte channel vector position `cv` and walks pixels, U packets
+// in flight.  Halo pixels are never read or written.
+// ================================================================================================
+struct GnP {
+    TV x, dy, o;                 // forward: x -> o;  backward: x, dy -> o (= dx)
+    int G; float eps; int act; float p_drop; float keep_scale; uint32_t thr16;
+    const uint64_t* rng; uint32_t layer;
+    const float* gamma; const float* beta;
+    double* stats;               // [N][G][2] (sum, sum of squares)
+    float* dgamma; float* dbeta; // backward: accumulated with atomics (may be NULL)
+    int accumulate;              // backward: dx += ...
+    int wshift;                  // log2(W) when W is a power of two, else -1
+};
+
+__device__ __forceinline__ void split_pix(int p, int W, int wshift, int& y, int& x) {
+    if (wshift >= 0) { y = p >> wshift; x = p & (W - 1); }
+    else { y = p / W; x = p - y * W; }
 }
 
-extern "C" int ddpm_gn_stats(const ddpm_tensor* x, int dtype, int groups, double* stats, void* stream) {
-    if (!tensor_ok(x) || !stats || groups <= 0 || x->C % groups) return DDPM_E_ARG;
-    cudaStream_t st = (cudaStream_t)stream;
-    CUDA_TRY(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * groups * x->N, st));
-    TV v(*x);
-    int HW = x->H * x->W;
-    size_t sm = sizeof(double) * 2 * groups;
-#define GO(T, VEC) { int cvs = x->C / VEC; if (cvs > NT) return DDPM_E_ARG; int ppi = NT / cvs; \
-        dim3 grid(blocks_per_image(x->N, HW, ppi * 8), x->N); \
-        gn_stats_kernel<T, VEC><<<grid, NT, sm, st>>>(v, groups, stats); }
-    if (dtype == DDPM_BF16) { if (vec_ok(x, 8, 2)) GO(bf16, 8) else GO(bf16, 1) }
-    else if (dtype == DDPM_F32) { if (vec_ok(x, 4, 4)) GO(float, 4) else GO(float, 1) }
-    else return DDPM_E_ARG;
-#undef GO
+// CTA-wide reduction of NV per-thread partial sums per channel-vector element:
+// part[k][tid] -> chan[k / VEC][c], c = cv*VEC + (k % VEC), summed over the threads that share `cv`.
+template <int VEC, int NSTAT>
+__device__ __forceinline__ void cta_channel_reduce(float (*part)[NT], const float* vals, double* chan, int C, const PixMap& m) {
+#pragma unroll
+    for (int k = 0; k < NSTAT * VEC; ++k) part[k][threadIdx.x] = vals[k];
+    __syncthreads();
+    for (int o = threadIdx.x; o < NSTAT * C; o += NT) {
+        const int st = o / C, c = o - st * C;
+        const int cv = c / VEC, k = c - cv * VEC;
+        double a = 0.0;
+        for (int r = 0; r < m.ppi; ++r) a += (double)part[st * VEC + k][r * m.cvs + cv];
+        chan[o] = a;
+    }
+    __syncthreads();
+}
+
+// MODE 0: fused stats + apply; 1: stats only; 2: apply only (stats given)
+template <typename T, int VEC, int MODE>
+__global__ void __launch_bounds__(NT, 3) gn_fwd_kernel(GnP a) {
+    extern __shared__ __align__(16) unsigned char gsm[];
+    const int C = a.x.C, G = a.G, cpg = C / G, HW = a.x.H * a.x.W, W = a.x.W;
+    double* chan = reinterpret_cast<double*>(gsm);           // [2][C]
+    double* gpart = chan + 2 * C;                            // [2][G]  (read by the other CTAs of the cluster)
+    float* gm = reinterpret_cast<float*>(gpart + 2 * G);     // [G] mean
+    float* gr = gm + G;                                      // [G] rstd
+    __shared__ float part[2 * VEC][NT];
+    cg::cluster_group cl = cg::this_cluster();
+    const int CS = (int)cl.num_blocks(), rank = (int)cl.block_rank();
+    const int n = blockIdx.x / CS;
+    const PixMap m = make_map<VEC>(C);
+    const int per = (HW + CS - 1) / CS;
+    const int p0 = rank * per, p1 = min(HW, p0 + per);
+    const int c0 = m.cv * VEC;
+    constexpr int U = 8;
+
+    if (MODE != 2) {
+        float acc[2 * VEC];
+#pragma unroll
+        for (int i = 0; i < 2 * VEC; ++i) acc[i] = 0.f;
+        if (m.active) {
+            for (int pb = p0 + m.prow; pb < p1; pb += U * m.ppi) {
+                Raw<T, VEC> r[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int p = pb + u * m.ppi;
+                    if (p < p1) { int y, xx; split_pix(p, W, a.wshift, y, xx); ldraw<T, VEC>(a.x.at<T>(n, y, xx, c0), r[u]); }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (pb + u * m.ppi < p1) {
+                        float v[VEC];
+                        unraw<T, VEC>(r[u], v);
+#pragma unroll
+                        for (int i = 0; i < VEC; ++i) { acc[i] += v[i]; acc[VEC + i] = fmaf(v[i], v[i], acc[VEC + i]); }
+                    }
+                }
+            }
+        }
+        cta_channel_reduce<VEC, 2>(part, acc, chan, C, m);
+        for (int o = threadIdx.x; o < 2 * G; o += NT) {
+            const int st = o / G, g = o - st * G;
+            double s = 0.0;
+            for (int j = 0; j < cpg; ++j) s += chan[st * C + g * cpg + j];
+            gpart[o] = s;
+        }
+        cluster_arrive(); cluster_wait();                    // every CTA's gpart is complete
+        for (int g = threadIdx.x; g < G; g += NT) {
+            double s = 0.0, q = 0.0;
+            for (int r = 0; r < CS; ++r) {
+                const double* rp = cl.map_shared_rank(gpart, r);
+                s += rp[g]; q += rp[G + g];
+            }
+            if (rank == 0) { a.stats[((size_t)n * G + g) * 2] = s; a.stats[((size_t)n * G + g) * 2 + 1] = q; }
+            const double cnt = (double)cpg * HW, mu = s / cnt;
+            double var = q / cnt - mu * mu; if (var < 0.0) var = 0.0;
+            gm[g] = (float)mu; gr[g] = (float)(1.0 / sqrt(var + (double)a.eps));
+        }
+        cluster_arrive();                                    // remote reads done; waited for before exit
+        __syncthreads();
+    } else {
+        for (int g = threadIdx.x; g < G; g += NT) {
+            const double s = a.stats[((size_t)n * G + g) * 2], q = a.stats[((size_t)n * G + g) * 2 + 1];
+            const double cnt = (double)cpg * HW, mu = s / cnt;
+            double var = q / cnt - mu * mu; if (var < 0.0) var = 0.0;
+            gm[g] = (float)mu; gr[g] = (float)(1.0 / sqrt(var + (double)a.eps));
+        }
+        __syncthreads();
+    }
+
+    if (MODE != 1 && m.active) {
+        float sc[VEC], sh[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            const int c = c0 + i, g = c / cpg;
+            sc[i] = gr[g] * __ldg(a.gamma + c);
+            sh[i] = __ldg(a.beta + c) - gm[g] * sc[i];
+        }
+        for (int pb = p0 + m.prow; pb < p1; pb += U * m.ppi) {
+            Raw<T, VEC> r[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int p = pb + u * m.ppi;
+                if (p < p1) { int y, xx; split_pix(p, W, a.wshift, y, xx); ldraw<T, VEC>(a.x.at<T>(n, y, xx, c0), r[u]); }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int p = pb + u * m.ppi;
+                if (p < p1) {
+                    float v[VEC];
+                    unraw<T, VEC>(r[u], v);
+                    uint32_t keep = 0xffffffffu;
+                    if (a.thr16) keep = dropout_mask16<VEC>(a.rng, a.layer, ((uint64_t)n * HW + p) * C + c0, a.thr16);
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) {
+                        float z = fmaf(v[i], sc[i], sh[i]);
+                        if (a.act) z = silu_f(z);
+                        v[i] = ((keep >> i) & 1u) ? z * a.keep_scale : 0.f;
+                    }
+                    int y, xx; split_pix(p, W, a.wshift, y, xx);
+                    stv<T, VEC>(a.o.at<T>(n, y, xx, c0), v);
+                }
+            }
+        }
+    }
+    if (MODE != 2) cluster_wait();                           // do not exit while peers may still read gpart
+}
+
+// backward: z = x*sc+sh, y = drop(act(z)); dz = dy * mask/(1-p) * act'(z)
+//   S1[c] = sum_p dz, S2[c] = sum_p dz*xhat;  A_g = mean_g(gamma*S1), B_g = mean_g(gamma*S2)
+//   dx = rstd * (dz*gamma - A_g - xhat*B_g);  dbeta += S1, dgamma += S2
+template <typename T, int VEC>
+__global__ void __launch_bounds__(NT, 2) gn_bwd_kernel(GnP a) {
+    extern __shared__ __align__(16) unsigned char gsm[];
+    const int C = a.x.C, G = a.G, cpg = C / G, HW = a.x.H * a.x.W, W = a.x.W;
+    double* chan = reinterpret_cast<double*>(gsm);           // [2][C] this CTA's per-channel partials (read by peers)
+    float* tot = reinterpret_cast<float*>(chan + 2 * C);     // [2][C] cluster totals
+    float* gA = tot + 2 * C;                                 // [G]
+    float* gB = gA + G;                                      // [G]
+    float* gm = gB + G;                                      // [G] mean
+    float* gr = gm + G;                                      // [G] rstd
+    __shared__ float part[2 * VEC][NT];
+    cg::cluster_group cl = cg::this_cluster();
+    const int CS = (int)cl.num_blocks(), rank = (int)cl.block_rank();
+    const int n = blockIdx.x / CS;
+    const PixMap m = make_map<VEC>(C);
+    const int per = (HW + CS - 1) / CS;
+    const int p0 = rank * per, p1 = min(HW, p0 + per);
+    const int c0 = m.cv * VEC;
+    constexpr int U = 4;
+
+    for (int g = threadIdx.x; g < G; g += NT) {
+        const double s = a.stats[((size_t)n * G + g) * 2], q = a.stats[((size_t)n * G + g) * 2 + 1];
+        const double cnt = (double)cpg * HW, mu = s / cnt;
+        double var = q / cnt - mu * mu; if (var < 0.0) var = 0.0;
+        gm[g] = (float)mu; gr[g] = (float)(1.0 / sqrt(var + (double)a.eps));
+    }
+    __syncthreads();
+    float rs[VEC], mr[VEC], ga[VEC], be[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        const int c = min(c0 + i, C - 1), g = c / cpg;
+        rs[i] = gr[g]; mr[i] = gm[g] * gr[g]; ga[i] = __ldg(a.gamma + c); be[i] = __ldg(a.beta + c);
+    }
+
+    // ---- phase 1: per-channel sums
+    {
+        float acc[2 * VEC];
+#pragma unroll
+        for (int i = 0; i < 2 * VEC; ++i) acc[i] = 0.f;
+        if (m.active) {
+            for (int pb = p0 + m.prow; pb < p1; pb += U * m.ppi) {
+                Raw<T, VEC> rx[U], rd[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int p = pb + u * m.ppi;
+                    if (p < p1) {
+                        int y, xx; split_pix(p, W, a.wshift, y, xx);
+                        ldraw<T, VEC>(a.x.at<T>(n, y, xx, c0), rx[u]);
+                        ldraw<T, VEC>(a.dy.at<T>(n, y, xx, c0), rd[u]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int p = pb + u * m.ppi;
+                    if (p < p1) {
+                        float v[VEC], d[VEC];
+                        unraw<T, VEC>(rx[u], v); unraw<T, VEC>(rd[u], d);
+                        uint32_t keep = 0xffffffffu;
+                        if (a.thr16) keep = dropout_mask16<VEC>(a.rng, a.layer, ((uint64_t)n * HW + p) * C + c0, a.thr16);
+#pragma unroll
+                        for (int i = 0; i < VEC; ++i) {
+                            const float xh = fmaf(v[i], rs[i], -mr[i]);
+                            float dz = ((keep >> i) & 1u) ? d[i] * a.keep_scale : 0.f;
+                            if (a.act) dz *= dsilu_f(fmaf(xh, ga[i], be[i]));
+                            acc[i] += dz; acc[VEC + i] = fmaf(dz, xh, acc[VEC + i]);
+                        }
+                    }
+                }
+            }
+        }
+        cta_channel_reduce<VEC, 2>(part, acc, chan, C, m);
+    }
+    cluster_arrive(); cluster_wait();                        // every CTA's chan[] is complete
+    for (int o = threadIdx.x; o < 2 * C; o += NT) {
+        double s = 0.0;
+        for (int r = 0; r < CS; ++r) s += cl.map_shared_rank(chan, r)[o];
+        tot[o] = (float)s;
+        if (rank == 0) {
+            if (o < C) { if (a.dbeta) atomicAdd(a.dbeta + o, (float)s); }
+            else if (a.dgamma) atomicAdd(a.dgamma + (o - C), (float)s);
+        }
+    }
+    cluster_arrive();                                        // remote reads done; waited for before exit
+    __syncthreads();
+    for (int g = threadIdx.x; g < G; g += NT) {
+        float sa = 0.f, sb = 0.f;
+        for (int j = 0; j < cpg; ++j) {
+            const int c = g * cpg + j;
+            const float gmm = __ldg(a.gamma + c);
+            sa = fmaf(gmm, tot[c], sa); sb = fmaf(gmm, tot[C + c], sb);
+        }
+        const float inv = 1.0f / ((float)cpg * (float)HW);
+        gA[g] = sa * inv; gB[g] = sb * inv;
+    }
+    __syncthreads();
+
+    // ---- phase 2: dx (x and dy are L2 hits now)
+    if (m.active) {
+        float ra[VEC], rb[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            const int g = min(c0 + i, C - 1) / cpg;
+            ra[i] = rs[i] * gA[g]; rb[i] = rs[i] * gB[g];
+        }
+        for (int pb = p0 + m.prow; pb < p1; pb += U * m.ppi) {
+            Raw<T, VEC> rx[U], rd[U], ro[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int p = pb + u * m.ppi;
+                if (p < p1) {
+                    int y, xx; split_pix(p, W, a.wshift, y, xx);
+                    ldraw<T, VEC>(a.x.at<T>(n, y, xx, c0), rx[u]);
+                    ldraw<T, VEC>(a.dy.at<T>(n, y, xx, c0), rd[u]);
+                    if (a.accumulate) ldraw<T, VEC>(a.o.at<T>(n, y, xx, c0), ro[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int p = pb + u * m.ppi;
+                if (p < p1) {
+                    float v[VEC], d[VEC], r[VEC];
+                    unraw<T, VEC>(rx[u], v); unraw<T, VEC>(rd[u], d);
+                    if (a.accumulate) unraw<T, VEC>(ro[u], r);
+                    uint32_t keep = 0xffffffffu;
+                    if (a.thr16) keep = dropout_mask16<VEC>(a.rng, a.layer, ((uint64_t)n * HW + p) * C + c0, a.thr16);
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) {
+                        const float xh = fmaf(v[i], rs[i], -mr[i]);
+                        float dz = ((keep >> i) & 1u) ? d[i] * a.keep_scale : 0.f;
+                        if (a.act) dz *= dsilu_f(fmaf(xh, ga[i], be[i]));
+                        const float g = fmaf(dz * ga[i], rs[i], -ra[i]) - xh * rb[i];     // rs*(dz*ga - A - xh*B)
+                        r[i] = a.accumulate ? r[i] + g : g;
+                    }
+                    int y, xx; split_pix(p, W, a.wshift, y, xx);
+                    stv<T, VEC>(a.o.at<T>(n, y, xx, c0), r);
+                }
+            }
+        }
+    }
+    cluster_wait();
+}
+
+// cluster size: enough CTAs per image that a thread sees ~16 packets per phase, at most 8 (portable limit)
+static int gn_cluster_size(int HW, int cvs) {
+    const int64_t packets = (int64_t)HW * cvs;
+    int cs = 1;
+    while (cs < 8 && packets / (cs * NT) >= 24) cs <<= 1;
+    return cs;
+}
+static int log2_exact(int v) { int s = 0; while ((1 << s) < v) ++s; return (1 << s) == v ? s : -1; }
+
+template <typename K>
+static int launch_cluster(K kernel, int grid, int cs, size_t smem, cudaStream_t st, GnP& p) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, p);
+    if (e != cudaSuccess) return (int)e;
     LAUNCH_OK();
     return 0;
 }
 
-// per-channel affine tables for image n:  y = x*scale + shift ; xhat = x*rstd - mean*rstd
-__device__ __forceinline__ void group_moments(const double* stats, int n, int G, int g, double cnt, float eps,
-                                              float* mean, float* rstd) {
-    double s = stats[((size_t)n * G + g) * 2], q = stats[((size_t)n * G + g) * 2 + 1];
-    double mu = s / cnt;
-    double var = q / cnt - mu * mu;
-    if (var < 0.0) var = 0.0;
-    *mean = (float)mu;
-    *rstd = (float)(1.0 / sqrt(var + (double)eps));
+static int gn_fill(GnP& p, const ddpm_tensor* x, int groups, const double* stats, const float* gamma, const float* beta,
+                   float eps, int act, float p_drop, const uint64_t* rng, uint32_t layer) {
+    if (p_drop > 0.f && !rng) return DDPM_E_ARG;
+    if (p_drop < 0.f || p_drop >= 1.f) return DDPM_E_ARG;
+    p.x = TV(*x); p.G = groups; p.eps = eps; p.act = act; p.p_drop = p_drop;
+    p.thr16 = p_drop > 0.f ? (uint32_t)(p_drop * 65536.0f + 0.5f) : 0u;
+    p.keep_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
+    p.rng = rng; p.layer = layer; p.gamma = gamma; p.beta = beta; p.stats = const_cast<double*>(stats);
+    p.dgamma = p.dbeta = nullptr; p.accumulate = 0; p.wshift = log2_exact(x->W);
+    return 0;
 }
 
-// ------------------------------------------------------------------------------------ gn_apply
-template <typename T, int VEC>
-__global__ void __launch_bounds__(NT, 4) gn_apply_kernel(TV x, TV o, int G, const double* stats, const float* gamma,
-                                                      const float* beta, float eps, int act, float p_drop,
-                                                      const uint64_t* rng, uint32_t layer) {
-    extern __shared__ float tb[];            // scale[C], shift[C]
-    const int n = blockIdx.y, C = x.C, cpg = C / G, HW = x.H * x.W;
-    float* scale = tb; float* shift = tb + C;
-    for (int c = threadIdx.x; c < C; c += NT) {
-        float mu, rs;
-        group_moments(stats, n, G, c / cpg, (double)cpg * HW, eps, &mu, &rs);
-        float sc = rs * gamma[c];
-        scale[c] = sc; shift[c] = beta[c] - mu * sc;
-    }
-    __syncthreads();
-    PixMap m = make_map<VEC>(C);
-    if (!m.active) return;
-    float sc[VEC], sh[VEC];
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) { sc[i] = scale[m.cv * VEC + i]; sh[i] = shift[m.cv * VEC + i]; }
-    const float keep_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
-    const int per = (HW + gridDim.x - 1) / gridDim.x;
-    const int p0 = blockIdx.x * per, p1 = min(HW, p0 + per);
-    constexpr int U = 2;
-    for (int pb = p0 + m.prow; pb < p1; pb += U * m.ppi) {
-        float v[U][VEC];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            int p = pb + u * m.ppi;
-            if (p < p1) { int y = p / x.W, xx = p - y * x.W; ldv<T, VEC>(x.at<T>(n, y, xx, m.cv * VEC), v[u]); }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            int p = pb + u * m.ppi;
-            if (p >= p1) break;
-            uint32_t keep = 0xffffffffu;
-            if (p_drop > 0.f) keep = dropout_mask<VEC>(rng, layer, ((uint64_t)n * HW + p) * C + m.cv * VEC, p_drop);
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) {
-                float z = fmaf(v[u][i], sc[i], sh[i]);
-                if (act) z = silu_f(z);
-                v[u][i] = ((keep >> i) & 1u) ? z * keep_scale : 0.f;
-            }
-            int y = p / x.W, xx = p - y * x.W;
-            stv<T, VEC>(o.at<T>(n, y, xx, m.cv * VEC), v[u]);
-        }
-    }
+template <int MODE>
+static int gn_fwd_dispatch(GnP& p, const ddpm_tensor* x, const ddpm_tensor* out, int dtype, cudaStream_t st) {
+    const int HW = x->H * x->W, C = x->C, G = p.G;
+    const size_t sm = sizeof(double) * (2 * C + 2 * G) + sizeof(float) * 2 * G;
+#define GO(T, VEC) { int cvs = C / VEC; if (cvs > NT) return DDPM_E_ARG; \
+        int cs = MODE == 2 ? 1 : gn_cluster_size(HW, cvs); \
+        if (MODE == 2) { cs = 1; int want = (HW * cvs) / (NT * 16); while (cs < 8 && cs < want) cs <<= 1; } \
+        return launch_cluster(gn_fwd_kernel<T, VEC, MODE>, x->N * cs, cs, sm, st, p); }
+    const bool v8 = vec_ok(x, 8, 2) && (MODE == 1 || vec_ok(out, 8, 2));
+    const bool v4 = vec_ok(x, 4, 4) && (MODE == 1 || vec_ok(out, 4, 4));
+    if (dtype == DDPM_BF16) { if (v8) GO(bf16, 8) else GO(bf16, 1) }
+    else if (dtype == DDPM_F32) { if (v4) GO(float, 4) else GO(float, 1) }
+#undef GO
+    return DDPM_E_ARG;
+}
+
+extern "C" int ddpm_gn_stats(const ddpm_tensor* x, int dtype, int groups, double* stats, void* stream) {
+    if (!tensor_ok(x) || !stats || groups <= 0 || x->C % groups) return DDPM_E_ARG;
+    GnP p; int rc = gn_fill(p, x, groups, stats, nullptr, nullptr, 0.f, 0, 0.f, nullptr, 0); if (rc) return rc;
+    p.o = p.x; p.dy = p.x;
+    return gn_fwd_dispatch<1>(p, x, x, dtype, (cudaStream_t)stream);
 }
 
 extern "C" int ddpm_gn_apply(const ddpm_tensor* x, int dtype, int groups, const double* stats, const float* gamma,
@@ -172,167 +443,40 @@ extern "C" int ddpm_gn_apply(const ddpm_tensor* x, int dtype, int groups, const 
                              uint32_t layer_id, const ddpm_tensor* out, void* stream) {
     if (!tensor_ok(x) || !tensor_ok(out) || !stats || !gamma || !beta || groups <= 0 || x->C % groups) return DDPM_E_ARG;
     if (out->N != x->N || out->H != x->H || out->W != x->W || out->C != x->C) return DDPM_E_ARG;
-    if (p_drop > 0.f && !rng) return DDPM_E_ARG;
-    if (p_drop < 0.f || p_drop >= 1.f) return DDPM_E_ARG;
-    cudaStream_t st = (cudaStream_t)stream;
-    TV v(*x), o(*out);
-    int HW = x->H * x->W;
-    size_t sm = sizeof(float) * 2 * x->C;
-#define GO(T, VEC) { int cvs = x->C / VEC; if (cvs > NT) return DDPM_E_ARG; int ppi = NT / cvs; \
-        dim3 grid(blocks_per_image(x->N, HW, ppi * 4), x->N); \
-        gn_apply_kernel<T, VEC><<<grid, NT, sm, st>>>(v, o, groups, stats, gamma, beta, eps, act, p_drop, rng, layer_id); }
-    if (dtype == DDPM_BF16) { if (vec_ok(x, 8, 2) && vec_ok(out, 8, 2)) GO(bf16, 8) else GO(bf16, 1) }
-    else if (dtype == DDPM_F32) { if (vec_ok(x, 4, 4) && vec_ok(out, 4, 4)) GO(float, 4) else GO(float, 1) }
-    else return DDPM_E_ARG;
-#undef GO
-    LAUNCH_OK();
-    return 0;
+    GnP p; int rc = gn_fill(p, x, groups, stats, gamma, beta, eps, act, p_drop, rng, layer_id); if (rc) return rc;
+    p.o = TV(*out); p.dy = p.x;
+    return gn_fwd_dispatch<2>(p, x, out, dtype, (cudaStream_t)stream);
 }
 
-// ------------------------------------------------------------------------------------ gn_bwd
-// z = x*scale+shift, y = drop(act(z)).  dz = dy * mask/(1-p) * act'(z).
-// pass 1: ws[n][c] = (sum_p dz, sum_p dz*xhat).
-template <typename T, int VEC>
-__global__ void __launch_bounds__(NT, 4) gn_bwd_reduce_kernel(TV x, TV dy, int G, const double* stats, const float* gamma,
-                                                              const float* beta, float eps, int act, float p_drop,
-                                                              const uint64_t* rng, uint32_t layer, float* ws) {
-    extern __shared__ float tb[];            // rs[C], mr[C], ga[C], be[C], s1[C], s2[C]
-    const int n = blockIdx.y, C = x.C, cpg = C / G, HW = x.H * x.W;
-    float* rsv = tb; float* mrv = tb + C; float* gav = tb + 2 * C; float* bev = tb + 3 * C;
-    float* a1 = tb + 4 * C; float* a2 = tb + 5 * C;
-    for (int c = threadIdx.x; c < C; c += NT) {
-        float mu, rs;
-        group_moments(stats, n, G, c / cpg, (double)cpg * HW, eps, &mu, &rs);
-        rsv[c] = rs; mrv[c] = mu * rs; gav[c] = gamma[c]; bev[c] = beta[c]; a1[c] = 0.f; a2[c] = 0.f;
-    }
-    __syncthreads();
-    PixMap m = make_map<VEC>(C);
-    if (m.active) {
-        float s1[VEC], s2[VEC];
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
-        const int c0 = m.cv * VEC;
-        const float keep_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
-        const int per = (HW + gridDim.x - 1) / gridDim.x;
-        const int p0 = blockIdx.x * per, p1 = min(HW, p0 + per);
-        for (int p = p0 + m.prow; p < p1; p += m.ppi) {
-            int y = p / x.W, xx = p - y * x.W;
-            float v[VEC], d[VEC];
-            ldv<T, VEC>(x.at<T>(n, y, xx, c0), v);
-            ldv<T, VEC>(dy.at<T>(n, y, xx, c0), d);
-            uint32_t keep = 0xffffffffu;
-            if (p_drop > 0.f) keep = dropout_mask<VEC>(rng, layer, ((uint64_t)n * HW + p) * C + c0, p_drop);
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) {
-                float xh = fmaf(v[i], rsv[c0 + i], -mrv[c0 + i]);
-                float dz = ((keep >> i) & 1u) ? d[i] * keep_scale : 0.f;
-                if (act) dz *= dsilu_f(fmaf(xh, gav[c0 + i], bev[c0 + i]));
-                s1[i] += dz; s2[i] = fmaf(dz, xh, s2[i]);
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-            atomicAdd(&a1[c0 + i], s1[i]);
-            atomicAdd(&a2[c0 + i], s2[i]);
-        }
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < C; c += NT) {
-        atomicAdd(&ws[((size_t)n * C + c) * 2], a1[c]);
-        atomicAdd(&ws[((size_t)n * C + c) * 2 + 1], a2[c]);
-    }
-}
-
-// pass 2: dx = rstd * (dz*gamma - A_g - xhat*B_g),  A_g = mean_g(gamma*S1), B_g = mean_g(gamma*S2)
-template <typename T, int VEC>
-__global__ void __launch_bounds__(NT, 4) gn_bwd_apply_kernel(TV x, TV dy, TV dx, int G, const double* stats,
-                                                             const float* gamma, const float* beta, float eps, int act,
-                                                             float p_drop, const uint64_t* rng, uint32_t layer,
-                                                             const float* ws, int accumulate) {
-    extern __shared__ float tb[];            // rs[C], mr[C], ga[C], be[C], ra[C] (= rs*A_g), rb[C] (= rs*B_g), ag[G], bg[G]
-    const int n = blockIdx.y, C = x.C, cpg = C / G, HW = x.H * x.W;
-    float* rsv = tb; float* mrv = tb + C; float* gav = tb + 2 * C; float* bev = tb + 3 * C;
-    float* rav = tb + 4 * C; float* rbv = tb + 5 * C; float* ag = tb + 6 * C; float* bg = ag + G;
-    for (int g = threadIdx.x; g < G; g += NT) {
-        float a = 0.f, b = 0.f;
-        for (int j = 0; j < cpg; ++j) {
-            int c = g * cpg + j;
-            a += gamma[c] * ws[((size_t)n * C + c) * 2];
-            b += gamma[c] * ws[((size_t)n * C + c) * 2 + 1];
-        }
-        float inv = 1.0f / ((float)cpg * (float)HW);
-        ag[g] = a * inv; bg[g] = b * inv;
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < C; c += NT) {
-        float mu, rs;
-        group_moments(stats, n, G, c / cpg, (double)cpg * HW, eps, &mu, &rs);
-        rsv[c] = rs; mrv[c] = mu * rs; gav[c] = gamma[c]; bev[c] = beta[c];
-        rav[c] = rs * ag[c / cpg]; rbv[c] = rs * bg[c / cpg];
-    }
-    __syncthreads();
-    PixMap m = make_map<VEC>(C);
-    if (!m.active) return;
-    const int c0 = m.cv * VEC;
-    const float keep_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
-    const int per = (HW + gridDim.x - 1) / gridDim.x;
-    const int p0 = blockIdx.x * per, p1 = min(HW, p0 + per);
-    for (int p = p0 + m.prow; p < p1; p += m.ppi) {
-        int y = p / x.W, xx = p - y * x.W;
-        float v[VEC], d[VEC], r[VEC];
-        ldv<T, VEC>(x.at<T>(n, y, xx, c0), v);
-        ldv<T, VEC>(dy.at<T>(n, y, xx, c0), d);
-        if (accumulate) ldv<T, VEC>(dx.at<T>(n, y, xx, c0), r);
-        uint32_t keep = 0xffffffffu;
-        if (p_drop > 0.f) keep = dropout_mask<VEC>(rng, layer, ((uint64_t)n * HW + p) * C + c0, p_drop);
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-            float rs = rsv[c0 + i], ga = gav[c0 + i];
-            float xh = fmaf(v[i], rs, -mrv[c0 + i]);
-            float dz = ((keep >> i) & 1u) ? d[i] * keep_scale : 0.f;
-            if (act) dz *= dsilu_f(fmaf(xh, ga, bev[c0 + i]));
-            float g = fmaf(dz * ga, rs, -rav[c0 + i]) - xh * rbv[c0 + i];     // rs*(dz*ga - A - xh*B)
-            r[i] = accumulate ? r[i] + g : g;
-        }
-        stv<T, VEC>(dx.at<T>(n, y, xx, c0), r);
-    }
-}
-
-__global__ void gn_param_grad_kernel(const float* ws, int N, int C, float* dgamma, float* dbeta) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    float a = 0.f, b = 0.f;
-    for (int n = 0; n < N; ++n) { a += ws[((size_t)n * C + c) * 2]; b += ws[((size_t)n * C + c) * 2 + 1]; }
-    if (dbeta) dbeta[c] += a;
-    if (dgamma) dgamma[c] += b;
+extern "C" int ddpm_gn_fwd(const ddpm_tensor* x, int dtype, int groups, double* stats, const float* gamma,
+                           const float* beta, float eps, int act, float p_drop, const uint64_t* rng,
+                           uint32_t layer_id, const ddpm_tensor* out, void* stream) {
+    if (!tensor_ok(x) || !tensor_ok(out) || !stats || !gamma || !beta || groups <= 0 || x->C % groups) return DDPM_E_ARG;
+    if (out->N != x->N || out->H != x->H || out->W != x->W || out->C != x->C) return DDPM_E_ARG;
+    GnP p; int rc = gn_fill(p, x, groups, stats, gamma, beta, eps, act, p_drop, rng, layer_id); if (rc) return rc;
+    p.o = TV(*out); p.dy = p.x;
+    return gn_fwd_dispatch<0>(p, x, out, dtype, (cudaStream_t)stream);
 }
 
 extern "C" int ddpm_gn_bwd(const ddpm_tensor* x, int dtype, int groups, const double* stats, const float* gamma,
                            const float* beta, float eps, int act, float p_drop, const uint64_t* rng,
                            uint32_t layer_id, const ddpm_tensor* dy, const ddpm_tensor* dx, int accumulate,
                            float* dgamma, float* dbeta, float* ws, void* stream) {
-    if (!tensor_ok(x) || !tensor_ok(dy) || !tensor_ok(dx) || !stats || !gamma || !beta || !ws) return DDPM_E_ARG;
+    (void)ws;                                  // kept in the signature for ABI stability; no longer needed
+    if (!tensor_ok(x) || !tensor_ok(dy) || !tensor_ok(dx) || !stats || !gamma || !beta) return DDPM_E_ARG;
     if (groups <= 0 || x->C % groups || dy->C != x->C || dx->C != x->C) return DDPM_E_ARG;
-    if (p_drop > 0.f && !rng) return DDPM_E_ARG;
+    if (dy->N != x->N || dy->H != x->H || dy->W != x->W || dx->N != x->N || dx->H != x->H || dx->W != x->W) return DDPM_E_ARG;
+    GnP p; int rc = gn_fill(p, x, groups, stats, gamma, beta, eps, act, p_drop, rng, layer_id); if (rc) return rc;
+    p.dy = TV(*dy); p.o = TV(*dx); p.accumulate = accumulate; p.dgamma = dgamma; p.dbeta = dbeta;
     cudaStream_t st = (cudaStream_t)stream;
-    CUDA_TRY(cudaMemsetAsync(ws, 0, sizeof(float) * 2 * x->C * x->N, st));
-    TV v(*x), d(*dy), o(*dx);
-    int HW = x->H * x->W, C = x->C;
-#define GO(T, VEC) { int cvs = C / VEC; if (cvs > NT) return DDPM_E_ARG; int ppi = NT / cvs; \
-        dim3 grid(blocks_per_image(x->N, HW, ppi * 4), x->N); \
-        gn_bwd_reduce_kernel<T, VEC><<<grid, NT, sizeof(float) * 6 * C, st>>>(v, d, groups, stats, gamma, beta, eps, act, p_drop, rng, layer_id, ws); \
-        LAUNCH_OK(); \
-        gn_bwd_apply_kernel<T, VEC><<<grid, NT, sizeof(float) * (6 * C + 2 * groups), st>>>(v, d, o, groups, stats, gamma, beta, eps, act, p_drop, rng, layer_id, ws, accumulate); \
-        LAUNCH_OK(); }
+    const int HW = x->H * x->W, C = x->C;
+    const size_t sm = sizeof(double) * 2 * C + sizeof(float) * (2 * C + 4 * groups);
+#define GO(T, VEC) { int cvs = C / VEC; if (cvs > NT) return DDPM_E_ARG; int cs = gn_cluster_size(HW, cvs); \
+        return launch_cluster(gn_bwd_kernel<T, VEC>, x->N * cs, cs, sm, st, p); }
     if (dtype == DDPM_BF16) { if (vec_ok(x, 8, 2) && vec_ok(dy, 8, 2) && vec_ok(dx, 8, 2)) GO(bf16, 8) else GO(bf16, 1) }
     else if (dtype == DDPM_F32) { if (vec_ok(x, 4, 4) && vec_ok(dy, 4, 4) && vec_ok(dx, 4, 4)) GO(float, 4) else GO(float, 1) }
-    else return DDPM_E_ARG;
 #undef GO
-    if (dgamma || dbeta) {
-        gn_param_grad_kernel<<<ceil_div(C, 128), 128, 0, st>>>(ws, x->N, C, dgamma, dbeta);
-        LAUNCH_OK();
-    }
-    return 0;
+    return DDPM_E_ARG;
 }
 
 // ------------------------------------------------------------------------------------ pixel maps

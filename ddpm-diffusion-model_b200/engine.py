@@ -39,12 +39,14 @@ class _Pool:
     def __init__(self):
         self.free: Dict[tuple, List[torch.Tensor]] = {}
         self.enabled = True
+        self.misses = 0           # allocations (each costs a cudaMalloc-cache lookup + a zero-fill kernel)
 
     def get(self, key, device):
         lst = self.free.get(key)
         if lst:
             return lst.pop()
         _, dt, shape = key
+        self.misses += 1
         return torch.zeros(shape, dtype=dt, device=device)
 
     def put(self, key, t):
@@ -296,13 +298,24 @@ def gn_apply(E: Exec, x: Act, st: torch.Tensor, gn: torch.nn.GroupNorm, act: int
     return out
 
 
+def gn_fwd(E: Exec, x: Act, gn: torch.nn.GroupNorm, act: int, p_drop: float, layer: int,
+           out: Optional[Act] = None):
+    """Fused stats + normalise + activation (+dropout): returns (out, stats)."""
+    if out is None:
+        out = E.act(x.N, x.H, x.W, x.C)
+    st = torch.empty((x.N, gn.num_groups, 2), dtype=torch.float64, device=E.device)
+    _lib.call("ddpm_gn_fwd", C.byref(x.desc()), x.dt, gn.num_groups, st.data_ptr(), gn.weight.data_ptr(),
+              gn.bias.data_ptr(), float(gn.eps), act, float(p_drop), E.rng.data_ptr() if p_drop > 0 else None,
+              layer, C.byref(out.desc()), E.stream)
+    return out, st
+
+
 def gn_bwd(E: Exec, x: Act, st: torch.Tensor, gn: torch.nn.GroupNorm, act: int, p_drop: float, layer: int,
            dy: Act, dx: Act, accumulate: bool) -> Act:
-    ws = E.f32(x.N, x.C, 2)
     _lib.call("ddpm_gn_bwd", C.byref(x.desc()), x.dt, gn.num_groups, st.data_ptr(), gn.weight.data_ptr(),
               gn.bias.data_ptr(), float(gn.eps), act, float(p_drop), E.rng.data_ptr() if p_drop > 0 else None,
               layer, C.byref(dy.desc()), C.byref(dx.desc()), 1 if accumulate else 0, _gptr(gn.weight),
-              _gptr(gn.bias), ws.data_ptr(), E.stream)
+              _gptr(gn.bias), None, E.stream)
     return dx
 
 
@@ -369,12 +382,10 @@ def resblock_fwd(E: Exec, blk, x: Act, tbias: torch.Tensor, out: Optional[Act] =
     """h = conv1(silu(gn1(x))) + b1 + tbias ; out = conv2(drop(silu(gn2(h)))) + b2 + skip(x)."""
     Cout = blk.out_ch
     p_drop = float(blk.drop.p) if (E.training and isinstance(blk.drop, torch.nn.Dropout)) else 0.0
-    st1 = gn_stats(E, x, blk.norm1.num_groups)
-    a1 = gn_apply(E, x, st1, blk.norm1, 1, 0.0, 0)
+    a1, st1 = gn_fwd(E, x, blk.norm1, 1, 0.0, 0)
     w1, _ = E.wcache.get(E, blk.conv1.weight, E.dt, E.need_grad)
     h = conv(E, a1, w1, E.act(x.N, x.H, x.W, Cout), 3, 1, 1, bias=blk.conv1.bias, tbias=tbias)
-    st2 = gn_stats(E, h, blk.norm2.num_groups)
-    a2 = gn_apply(E, h, st2, blk.norm2, 1, p_drop, layer)
+    a2, st2 = gn_fwd(E, h, blk.norm2, 1, p_drop, layer)
     w2, _ = E.wcache.get(E, blk.conv2.weight, E.dt, E.need_grad)
     if out is None:
         out = E.act(x.N, x.H, x.W, Cout)
@@ -427,8 +438,7 @@ def resblock_bwd(E: Exec, blk, saved, dout: Act, dx: Optional[Act] = None, dx_ac
 def attn_fwd(E: Exec, blk, x: Act, out: Optional[Act] = None):
     heads, d = blk.num_heads, blk.head_dim
     inner = heads * d
-    st = gn_stats(E, x, blk.norm.num_groups)
-    a = gn_apply(E, x, st, blk.norm, 0, 0.0, 0)
+    a, st = gn_fwd(E, x, blk.norm, 0, 0.0, 0)
     wq, _ = E.wcache.get(E, blk.qkv.weight, E.dt, E.need_grad)
     qkv = conv(E, a, wq, E.act(x.N, x.H, x.W, 3 * inner), 1)
     o = E.act(x.N, x.H, x.W, inner)
@@ -659,8 +669,7 @@ def unet_forward(E: Exec, model, x: torch.Tensor, t: torch.Tensor, out_dtype: to
                 tape.append(("res", blk, sv, i))
 
     # ---- head
-    st = gn_stats(E, cur, model.out_norm.num_groups)
-    a = gn_apply(E, cur, st, model.out_norm, 1, 0.0, 0)
+    a, st = gn_fwd(E, cur, model.out_norm, 1, 0.0, 0)
     w_out, _ = E.wcache.get(E, model.out_conv.weight, E.dt, G, cout_pad=cpad)
     oc = model.out_conv.out_channels
     y = conv(E, a, w_out, E.act(B, H, W, max(oc, cpad)), 3, 1, 1, bias=model.out_conv.bias)

@@ -98,8 +98,15 @@ int ddpm_gn_stats(const ddpm_tensor* x, int dtype, int groups, double* stats, vo
 int ddpm_gn_apply(const ddpm_tensor* x, int dtype, int groups, const double* stats, const float* gamma,
                   const float* beta, float eps, int act, float p_drop, const uint64_t* rng,
                   uint32_t layer_id, const ddpm_tensor* out, void* stream);
-/* backward of gn_apply.  ws: fp32 [N][C][2] scratch (zeroed by the call).  dx (+)= ...;
- * dgamma/dbeta (fp32 [C]) are accumulated. */
+/* gn_stats + gn_apply in ONE launch: a thread-block cluster per image reduces the moments over
+ * distributed shared memory, then re-reads the image (L2 hits) and writes `out`; `stats` is
+ * written for the backward pass.  4 B/elem of HBM traffic (bf16) instead of 6. */
+int ddpm_gn_fwd(const ddpm_tensor* x, int dtype, int groups, double* stats, const float* gamma,
+                const float* beta, float eps, int act, float p_drop, const uint64_t* rng,
+                uint32_t layer_id, const ddpm_tensor* out, void* stream);
+/* backward of gn_apply, one launch (cluster per image; reduce, exchange, re-read from L2, write).
+ * dx (+)= ...; dgamma/dbeta (fp32 [C]) are accumulated with atomics.  `ws` is unused (kept for
+ * ABI stability; may be NULL).  dx may alias dy. */
 int ddpm_gn_bwd(const ddpm_tensor* x, int dtype, int groups, const double* stats, const float* gamma,
                 const float* beta, float eps, int act, float p_drop, const uint64_t* rng,
                 uint32_t layer_id, const ddpm_tensor* dy, const ddpm_tensor* dx, int accumulate,
@@ -145,6 +152,9 @@ int ddpm_conv(const ddpm_conv_args* a, void* stream);
  * (0 = SWIZZLE_NONE, 1 = SWIZZLE_32B [+ descriptor base_offset]) */
 int ddpm_set_force_simt(int on);
 int ddpm_set_tc_mode(int mode, int base_offset);
+/* 1 (default): persistent CTA-pair kernel (tcgen05 cta_group::2, TMEM double buffering); 0: the
+ * first-generation one-tile-per-CTA kernel (kept for A/B measurements) */
+int ddpm_set_tc_v2(int on);
 
 typedef struct {
     ddpm_tensor act;   /* forward input operand of the conv */

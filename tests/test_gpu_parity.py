@@ -209,7 +209,8 @@ def test_conv_epilogues(pkg):
 
 
 @pytest.mark.parametrize("dt_name", ["f32", "bf16"])
-@pytest.mark.parametrize("shape", [(2, 32, 8, 8), (2, 96, 8, 8), (1, 288, 4, 4), (2, 64, 16, 16)])
+@pytest.mark.parametrize("shape", [(2, 32, 8, 8), (2, 96, 8, 8), (1, 288, 4, 4), (2, 64, 16, 16), (3, 96, 64, 64),
+                                   (2, 192, 16, 16), (2, 192, 32, 32), (2, 96, 12, 20)])
 @pytest.mark.parametrize("act", [0, 1])
 def test_groupnorm_fwd_bwd(pkg, shape, act, dt_name):
     _, _lib, engine = pkg
@@ -235,6 +236,10 @@ def test_groupnorm_fwd_bwd(pkg, shape, act, dt_name):
     st = engine.gn_stats(E, xa, gdev.num_groups)
     ya = engine.gn_apply(E, xa, st, gdev, act, 0.0, 0)
     assert rel(_from_act(pkg, E, ya), y) < tol
+    # fused stats+apply (one cluster per image) must agree with the two-launch path and the reference
+    yf, stf = engine.gn_fwd(E, xa, gdev, act, 0.0, 0)
+    assert rel(_from_act(pkg, E, yf), y) < tol
+    assert torch.allclose(stf, st, rtol=1e-6, atol=1e-6)
     dya = _to_act(pkg, E, dy)
     dxa = engine.gn_bwd(E, xa, st, gdev, act, 0.0, 0, dya, E.act(N, H, W, Cc), False)
     assert rel(_from_act(pkg, E, dxa), xr.grad) < tol
