@@ -110,6 +110,22 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
     return d;
 }
 
+// The MMA-issuing thread is a single lane: every integer instruction between two tcgen05.mma costs
+// ~5 cycles of dependent latency, and a loop that rebuilds both 64-bit descriptors (shifts, masks,
+// tap / 3, tap % 3) per MMA was measured at 137-230 cycles per MMA -- above the 48-128 cycle tensor
+// floor, i.e. the kernel was ISSUE-bound, independent of N (profiles/r1_conv_issue_bound.txt).
+// Descriptors are therefore split into a constant high word and a low word (address | LBO) that
+// advances by plain 32-bit adds.
+__device__ __forceinline__ uint64_t desc_pack(uint32_t lo, uint32_t hi) {
+    uint64_t d; asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi)); return d;
+}
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes, uint32_t layout) {
+    return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | ((layout & 7) << 29);
+}
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+    return ((saddr >> 4) & 0x3FFF) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+}
+
 // ------------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------------
@@ -371,7 +387,7 @@ static int conv_tc2_launch(const ddpm_conv_args* a, cudaStream_t st);
 extern int g_tc_v2_flag();
 int conv_tc_launch(const ddpm_conv_args* a, cudaStream_t st) {
     int rc = get_encode(); if (rc) return rc;
-    if (g_tc_v2_flag() && g_tc_mode == 1 && g_tc_exp == 0) return conv_tc2_launch(a, st);
+    if (g_tc_v2_flag() && g_tc_mode == 1) return conv_tc2_launch(a, st);
     const bool sw32 = g_tc_mode == 1;
     TcParams p;
     p.out = TV(a->out);
@@ -448,6 +464,11 @@ int conv_tc_launch(const ddpm_conv_args* a, cudaStream_t st) {
 //   tempty[b] (leader)  : 4 epilogue warps x 2 CTAs arrive (remote arrive from the peer)
 // ================================================================================================
 #define TC2_THREADS 192
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
     uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
@@ -497,10 +518,10 @@ struct Tc2Params {
     int S;                        // ring depth
     int a_chunk_bytes, b_chunk_bytes, stage_bytes;
     int pix_tiles, items;
-    int has_res, accum, sub;
+    int has_res, accum, sub, exp;
 };
 
-template <int MT>
+template <int MT, int TAPS>
 __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                     const __grid_constant__ CUtensorMap tmB, Tc2Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -546,51 +567,66 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_c
                     mbar_wait(&empty[s], ph ^ 1);
                     const int kc0 = st * p.KS, nk = min(p.KS, KCH - kc0);
                     const uint32_t fbar = mapa_u32(smem_u32(&full[s]), 0);
-                    if (leader) mbar_expect_tx(&full[s], (uint32_t)(2 * nk * (p.P * 32 + p.b_chunk_bytes)));
+                    const bool skipA = (p.exp & 1) && g >= (uint32_t)p.S, skipB = (p.exp & 2) && g >= (uint32_t)p.S;   // diagnostics
+                    const uint32_t tx = (uint32_t)(2 * nk * ((skipA ? 0 : p.P * 32) + (skipB ? 0 : p.b_chunk_bytes)));
+                    if (leader) { if (tx) mbar_expect_tx(&full[s], tx); else mbar_arrive(&full[s]); }
                     uint8_t* sbase = ring + (size_t)s * p.stage_bytes;
                     for (int k = 0; k < nk; ++k) {
                         uint8_t* adst = sbase + (size_t)k * (p.a_chunk_bytes + p.b_chunk_bytes);
                         uint8_t* bdst = adst + p.a_chunk_bytes;
                         const int row0 = Q0 - halo_rows;
-                        for (int r = 0; r < p.P; r += p.seg)
+                        for (int r = 0; r < p.P && !skipA; r += p.seg)
                             tma2_load_2d(adst + (size_t)r * 32, &tmA, fbar, (kc0 + k) * KC, row0 + r);
-                        tma2_load_3d(bdst, &tmB, fbar, (kc0 + k) * KC, nrow0, 0);
+                        if (!skipB) tma2_load_3d(bdst, &tmB, fbar, (kc0 + k) * KC, nrow0, 0);
                     }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================================================================== MMA issuer (leader CTA only)
-        if (leader && lane == 0) {
+        // the whole warp runs the loop (warp-uniform control flow keeps descriptors in uniform registers);
+        // one elected lane issues the tcgen05 instructions
+        if (leader) {
+            const bool el = elect_one();
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((256u >> 4) << 24);
+            const uint32_t hi = desc_hi(256u, 6u);                       // SBO 256 B, SWIZZLE_32B
+            uint32_t tapoff[TAPS];                                       // A row shift of each tap, in 16-byte units
+#pragma unroll
+            for (int tap = 0; tap < TAPS; ++tap) tapoff[tap] = TAPS == 9 ? (uint32_t)(((tap / 3) * p.Wp + (tap % 3)) * 2) : 0u;
+            const uint32_t b_tap = (uint32_t)p.NT;                       // (NT/2 rows * 32 B) >> 4
+            const uint32_t chunk16 = (uint32_t)((p.a_chunk_bytes + p.b_chunk_bytes) >> 4), a16 = (uint32_t)(p.a_chunk_bytes >> 4);
+            const uint32_t ring_lo = desc_lo(smem_u32(ring), 16u), stage16 = (uint32_t)(p.stage_bytes >> 4);
             uint32_t g = 0, j = 0;
             for (int it = pair; it < p.items; it += npairs, ++j) {
                 const uint32_t buf = j & 1, bph = (j >> 1) & 1;
                 mbar_wait(&tempty[buf], bph ^ 1);        // both CTAs' epilogues have drained this accumulator buffer
                 tc_fence_after();
                 const uint32_t dbase = tmem_base + buf * (uint32_t)cols_per_buf;
+                uint32_t acc = 0;
                 for (int st = 0; st < NST; ++st, ++g) {
-                    const int s = g % p.S; const uint32_t ph = (g / p.S) & 1;
+                    const uint32_t s = g % (uint32_t)p.S; const uint32_t ph = (g / (uint32_t)p.S) & 1;
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
-                    const int kc0 = st * p.KS, nk = min(p.KS, KCH - kc0);
-                    const uint32_t sbase = smem_u32(ring + (size_t)s * p.stage_bytes);
-                    for (int k = 0; k < nk; ++k) {
-                        const uint32_t a_base = sbase + (uint32_t)(k * (p.a_chunk_bytes + p.b_chunk_bytes));
-                        const uint32_t b_base = a_base + (uint32_t)p.a_chunk_bytes;
-                        for (int tap = 0; tap < p.taps; ++tap) {
-                            const int shift = (p.taps == 9) ? (tap / 3) * p.Wp + (tap % 3) : 0;
-                            const uint64_t bdesc = make_desc(b_base + (uint32_t)(tap * (p.NT / 2) * 32), 16u, 256u, 6u, 0);
+                    const int nk = min(p.KS, KCH - st * p.KS);
+                    uint32_t a_lo = ring_lo + s * stage16;
+                    for (int k = 0; k < nk; ++k, a_lo += chunk16) {
+                        const uint32_t b_lo = a_lo + a16;
+#pragma unroll
+                        for (int tap = 0; tap < TAPS; ++tap) {
+                            const uint64_t bdesc = desc_pack(b_lo + (uint32_t)tap * b_tap, hi);
 #pragma unroll
                             for (int mt = 0; mt < MT; ++mt) {
-                                const uint64_t adesc = make_desc(a_base + (uint32_t)((mt * 128 + shift) * 32), 16u, 256u, 6u, 0);
-                                umma2_bf16(dbase + (uint32_t)(mt * p.NT), adesc, bdesc, idesc, (st | k | tap) != 0 ? 1u : 0u);
+                                const uint64_t adesc = desc_pack(a_lo + tapoff[tap] + (uint32_t)(mt * 256), hi);
+                                if (el) umma2_bf16(dbase + (uint32_t)(mt * p.NT), adesc, bdesc, idesc, tap == 0 ? acc : 1u);
                             }
                         }
+                        acc = 1;
                     }
-                    umma2_commit_mc(&empty[s]);
+                    if (el) umma2_commit_mc(&empty[s]);
+                    __syncwarp();
                 }
-                umma2_commit_mc(&tfull[buf]);
+                if (el) umma2_commit_mc(&tfull[buf]);
+                __syncwarp();
             }
         }
     } else {
@@ -698,7 +734,7 @@ static int conv_tc2_launch(const ddpm_conv_args* a, cudaStream_t st) {
     p.Hp = a->in.H + 2; p.Wp = a->in.W + 2; p.H = a->in.H; p.W = a->in.W;
     p.Qtot = a->in.N * p.Hp * p.Wp;
     p.accum = (a->epi & DDPM_EPI_ACCUM) ? 1 : 0;
-    p.sub = a->stride == 2 ? 1 : 0;
+    p.sub = a->stride == 2 ? 1 : 0; p.exp = g_tc_exp;
     int MT = 256 / p.NT; if (MT > 2) MT = 2; if (MT < 1) MT = 1;
     // small problems: prefer more, smaller items so that every SM pair gets one
     if (MT == 2 && (int64_t)ceil_div(p.Qtot, 512) * p.n_tiles < sm_count() / 2) MT = 1;
@@ -739,14 +775,13 @@ static int conv_tc2_launch(const ddpm_conv_args* a, cudaStream_t st) {
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    static size_t configured[3] = {0, 0, 0};
-    if (MT == 2) {
-        if (smem > configured[2]) { CUDA_TRY(cudaFuncSetAttribute(conv_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured[2] = smem; }
-        CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<2>, tmA, tmB, p));
-    } else {
-        if (smem > configured[1]) { CUDA_TRY(cudaFuncSetAttribute(conv_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured[1] = smem; }
-        CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<1>, tmA, tmB, p));
-    }
+    static size_t configured[4] = {0, 0, 0, 0};
+#define TC2_GO(MTV, TAPSV, SLOT) { \
+        if (smem > configured[SLOT]) { CUDA_TRY(cudaFuncSetAttribute(conv_tc2_kernel<MTV, TAPSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured[SLOT] = smem; } \
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<MTV, TAPSV>, tmA, tmB, p)); }
+    if (MT == 2) { if (p.taps == 9) TC2_GO(2, 9, 0) else TC2_GO(2, 1, 1) }
+    else { if (p.taps == 9) TC2_GO(1, 9, 2) else TC2_GO(1, 1, 3) }
+#undef TC2_GO
     LAUNCH_OK();
     return 0;
 }
@@ -821,27 +856,37 @@ __global__ void __launch_bounds__(TC_THREADS) wgrad_tc_kernel(const __grid_const
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {   // whole warp, warp-uniform control flow; one elected lane issues tcgen05 instructions
+            const bool el = elect_one();
             // a_major = b_major = MN (bits 15, 16); M = 128; N = NT
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                                    ((uint32_t)(p.NT >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t hi = desc_hi(1024u, 2u);                      // SBO 1024 B, SWIZZLE_128B
+            const uint32_t y_lo0 = desc_lo(smem_u32(smem), (uint32_t)(WG_KQ * 128));
+            const uint32_t a_lo0 = desc_lo(smem_u32(smem) + (uint32_t)y_bytes, (uint32_t)(WG_ROWS * 128));
+            const uint32_t stage16 = (uint32_t)(p.stage_bytes >> 4);
+            const bool three = p.ntap == 3;
+            uint32_t acc = 0;
             for (int i = 0; i < nst; ++i) {
-                const int s = i % WG_STAGES; const uint32_t ph = (i / WG_STAGES) & 1;
+                const uint32_t s = (uint32_t)(i % WG_STAGES); const uint32_t ph = (i / WG_STAGES) & 1;
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
-                const uint32_t ybase = smem_u32(smem + (size_t)s * p.stage_bytes);
-                const uint32_t abase = ybase + (uint32_t)y_bytes;
+                const uint32_t y_lo = y_lo0 + s * stage16, a_lo = a_lo0 + s * stage16;
 #pragma unroll
                 for (int ks = 0; ks < WG_KQ / 16; ++ks) {
-                    const uint64_t ydesc = make_desc(ybase + (uint32_t)(ks * 16 * 128), (uint32_t)(WG_KQ * 128), 1024u, 2u, 0);
-                    for (int kx = 0; kx < p.ntap; ++kx) {
-                        const uint64_t adesc = make_desc(abase + (uint32_t)((ks * 16 + kx) * 128), (uint32_t)(WG_ROWS * 128), 1024u, 2u, 0);
-                        umma_bf16(tmem_base + (uint32_t)(kx * p.NT), ydesc, adesc, idesc, (i | ks) != 0 ? 1u : 0u);
+                    const uint64_t ydesc = desc_pack(y_lo + (uint32_t)(ks * 16 * 128 / 16), hi);
+                    if (el) umma_bf16(tmem_base, ydesc, desc_pack(a_lo + (uint32_t)((ks * 16) * 8), hi), idesc, ks == 0 ? acc : 1u);
+                    if (three && el) {
+                        umma_bf16(tmem_base + (uint32_t)p.NT, ydesc, desc_pack(a_lo + (uint32_t)((ks * 16 + 1) * 8), hi), idesc, ks == 0 ? acc : 1u);
+                        umma_bf16(tmem_base + (uint32_t)(2 * p.NT), ydesc, desc_pack(a_lo + (uint32_t)((ks * 16 + 2) * 8), hi), idesc, ks == 0 ? acc : 1u);
                     }
                 }
-                umma_commit(&empty[s]);
+                acc = 1;
+                if (el) umma_commit(&empty[s]);
+                __syncwarp();
             }
-            umma_commit(acc_full);
+            if (el) umma_commit(acc_full);
+            __syncwarp();
         }
     } else {
         const int qd = warp & 3;

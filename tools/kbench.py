@@ -67,34 +67,37 @@ def report(kind, name, sec, flops=None, nbytes=None, cnt=1):
 CONV = [(96, 96, 64, 5), (192, 192, 32, 5), (192, 192, 64, 1), (288, 96, 64, 1), (384, 192, 32, 1),
         (192, 192, 16, 6), (192, 192, 8, 9), (96, 192, 32, 1), (384, 192, 16, 1), (384, 192, 8, 1)]
 if args.shape:
-    ci, co, hw = [int(v) for v in args.shape.split(",")]
-    CONV = [(ci, co, hw, 1)]
+    CONV = []
+    for sh in args.shape.split(";"):
+        v = [int(t) for t in sh.split(",")]
+        CONV.append((v[0], v[1], v[2], 1) + ((v[3],) if len(v) > 3 else ()))
 GN = [(96, 64, 6), (96, 32, 1), (192, 32, 4), (192, 16, 5), (192, 8, 11), (384, 8, 1), (384, 16, 1), (384, 32, 1), (288, 64, 1)]
 
 E = engine.Exec(dev, _lib.BF16, True, True, rng=torch.tensor([1, 0], dtype=torch.int64, device=dev))
 
 if "conv" in only:
-    for ci, co, hw, cnt in CONV:
-        w = torch.nn.Parameter(torch.randn(co, ci, 3, 3, device=dev) * 0.02)
+    for ci, co, hw, cnt, *kk in CONV:
+        ks = kk[0] if kk else 3
+        w = torch.nn.Parameter(torch.randn(co, ci, ks, ks, device=dev) * 0.02)
         wf, _ = E.wcache.get(E, w, _lib.BF16, False)
         x = E.act(B, hw, hw, ci); x.interior().normal_()
         y = E.act(B, hw, hw, co)
-        fl = 2.0 * B * hw * hw * co * ci * 9
+        fl = 2.0 * B * hw * hw * co * ci * ks * ks
         modes = [(1, "")] + ([(1 | (1 << 4), " skipA"), (1 | (2 << 4), " skipB"), (1 | (3 << 4), " skipAB")] if args.exp else [])
         for mode, tag in modes:
             _lib.lib.ddpm_set_tc_mode(mode, 0)
-            sec = timeit(lambda: engine.conv(E, x, wf, y, 3, 1, 1))
-            report("conv", f"{ci}->{co}@{hw}{tag}", sec, flops=fl, cnt=2 * cnt)
+            sec = timeit(lambda: engine.conv(E, x, wf, y, ks, 1, ks // 2))
+            report("conv", f"{ci}->{co}@{hw}k{ks}{tag}", sec, flops=fl, cnt=2 * cnt)
         _lib.lib.ddpm_set_tc_mode(1, 0)
         if args.v1:
             _lib.lib.ddpm_set_tc_v2(0)
-            sec = timeit(lambda: engine.conv(E, x, wf, y, 3, 1, 1))
-            report("conv", f"{ci}->{co}@{hw} skip(v1 kernel)", sec, flops=fl, cnt=2 * cnt)
+            sec = timeit(lambda: engine.conv(E, x, wf, y, ks, 1, ks // 2))
+            report("conv", f"{ci}->{co}@{hw}k{ks} skip(v1 kernel)", sec, flops=fl, cnt=2 * cnt)
             _lib.lib.ddpm_set_tc_v2(1)
         del x, y
 
 if "wgrad" in only:
-    for ci, co, hw, cnt in CONV:
+    for ci, co, hw, cnt, *kk in CONV:
         w = torch.nn.Parameter(torch.zeros(co, ci, 3, 3, device=dev))
         x = E.act(B, hw, hw, ci); x.interior().normal_()
         dy = E.act(B, hw, hw, co); dy.interior().normal_()
