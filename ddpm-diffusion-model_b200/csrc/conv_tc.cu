@@ -463,7 +463,7 @@ int conv_tc_launch(const ddpm_conv_args* a, cudaStream_t st) {
 //   tfull[b]  (each CTA): commit multicast after the item's last MMA -> the CTA's own epilogue warps
 //   tempty[b] (leader)  : 4 epilogue warps x 2 CTAs arrive (remote arrive from the peer)
 // ================================================================================================
-#define TC2_THREADS 192
+#define TC2_THREADS 320          // warp 0 TMA, warp 1 MMA issue, warps 2..9 epilogue (two per TMEM lane quarter)
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
@@ -478,7 +478,10 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    // relaxed: the arrive only publishes "my tcgen05.ld of this accumulator buffer are done" (ordered by
+    // tcgen05.fence::before_thread_sync); a release here would also wait for the epilogue's global stores
+    // to drain (ncu: MEMBAR + ERRBAR = 16 % of the stall samples) for no reason
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tma2_load_2d(void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -519,6 +522,7 @@ struct Tc2Params {
     int a_chunk_bytes, b_chunk_bytes, stage_bytes;
     int pix_tiles, items;
     int has_res, accum, sub, exp;
+    int vec_bias, vec_tbias;      // 16-byte aligned -> float4 loads in the epilogue
 };
 
 template <int MT, int TAPS>
@@ -544,7 +548,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_c
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.S; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 8); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 16); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc2(tmem_slot, 512u);
@@ -631,7 +635,10 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_c
         }
     } else {
         // ===================================================================== epilogue (both CTAs)
-        const int qd = warp & 3;
+        const int qd = warp & 3;                          // TMEM lane quarter this warp may read (warp id % 4)
+        const int half = (warp - 2) >> 2;                 // the two warps of a quarter split the 16-column blocks
+        const int nblk = p.NT >> 4;
+        const int blk_lo = half ? (nblk + 1) / 2 : 0, blk_hi = half ? nblk : (nblk + 1) / 2;
         const int HpWp = p.Hp * p.Wp;
         const uint32_t tempty_leader0 = mapa_u32(smem_u32(&tempty[0]), 0);
         const uint32_t tempty_leader1 = mapa_u32(smem_u32(&tempty[1]), 0);
@@ -645,7 +652,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_c
             tc_fence_after();
             const uint32_t dbase = tmem_base + buf * (uint32_t)cols_per_buf;
 #pragma unroll 1
-            for (int mt = 0; mt < MT; ++mt) {
+            for (int mt = 0; mt < ((p.exp & 4) ? 0 : MT); ++mt) {      // exp bit 2: skip the epilogue (diagnostic)
                 const int Q = Q0 + mt * 128 + qd * 32 + lane;
                 bool valid = Q < p.Qtot;
                 int n = 0, y = 0, x = 0;
@@ -658,53 +665,87 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_c
                 bf16* orow = valid ? p.out.at<bf16>(n, y, x, n0) : nullptr;
                 const bf16* rrow = (valid && p.has_res) ? p.res.at<bf16>(n, y, x, n0) : nullptr;
                 const float* tb = (valid && p.tbias) ? p.tbias + (size_t)n * p.tbias_pitch + n0 : nullptr;
+                // (staging the tile in shared memory to emit full 128-byte lines per store instruction was measured
+                // SLOWER -- 153 vs 117 us at 96->96@64: the kernel is bound by L2 traffic, not store coalescing)
+                // 64 output channels per trip: all TMEM / residual / accumulate loads of the trip are in flight
+                // before the first use, so one L2 round trip is exposed per trip instead of per 16 columns
 #pragma unroll 1
-                for (int c0 = 0; c0 < p.NT; c0 += 16) {
-                    uint32_t r[16];
-                    tmem_ld16(dbase + ((uint32_t)(qd * 32) << 16) + (uint32_t)(mt * p.NT + c0), r);
+                constexpr int EB = 2;                         // 16-column blocks per trip (register budget: 320 threads)
+                for (int blk = blk_lo; blk < blk_hi; blk += EB) {
+                    uint32_t r[EB][16];
+                    uint4 rr[EB][2], ra[EB][2];
+#pragma unroll
+                    for (int q = 0; q < EB; ++q) {
+                        const int c = (blk + q) << 4;
+                        if (blk + q < blk_hi) {
+                            tmem_ld16(dbase + ((uint32_t)(qd * 32) << 16) + (uint32_t)(mt * p.NT + c), r[q]);
+                            if (rrow) { rr[q][0] = *reinterpret_cast<const uint4*>(rrow + c); rr[q][1] = *reinterpret_cast<const uint4*>(rrow + c + 8); }
+                            if (p.accum && valid) { ra[q][0] = *reinterpret_cast<const uint4*>(orow + c); ra[q][1] = *reinterpret_cast<const uint4*>(orow + c + 8); }
+                        }
+                    }
                     tmem_ld_wait();
-                    if (valid && n0 + c0 < p.Cout) {
-                        float v[16];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-                        if (p.bias) {
+                    for (int q = 0; q < EB; ++q) {
+                        const int c = (blk + q) << 4;
+                        if (blk + q < blk_hi && valid && n0 + c < p.Cout) {
+                            float v[16];
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) if (n0 + c0 + i < p.bias_n) v[i] += __ldg(p.bias + n0 + c0 + i);
-                        }
-                        if (tb) {
+                            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[q][i]);
+                            if (p.bias) {
+                                if (p.vec_bias && n0 + c + 16 <= p.bias_n) {
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) v[i] += __ldg(tb + c0 + i);
-                        }
-                        if (rrow) {
-                            uint4 a = *reinterpret_cast<const uint4*>(rrow + c0), b = *reinterpret_cast<const uint4*>(rrow + c0 + 8);
-                            const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
-                            const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&b);
+                                    for (int i = 0; i < 16; i += 4) {
+                                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c + i));
+                                        v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int i = 0; i < 16; ++i) if (n0 + c + i < p.bias_n) v[i] += __ldg(p.bias + n0 + c + i);
+                                }
+                            }
+                            if (tb) {
+                                if (p.vec_tbias) {
+#pragma unroll
+                                    for (int i = 0; i < 16; i += 4) {
+                                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(tb + c + i));
+                                        v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int i = 0; i < 16; ++i) v[i] += __ldg(tb + c + i);
+                                }
+                            }
+                            if (rrow) {
+                                const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&rr[q][0]);
+                                const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&rr[q][1]);
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    float2 fa = __bfloat1622float2(ha[i]), fb = __bfloat1622float2(hb[i]);
+                                    v[2 * i] += fa.x; v[2 * i + 1] += fa.y; v[8 + 2 * i] += fb.x; v[8 + 2 * i + 1] += fb.y;
+                                }
+                            }
+                            if (p.accum) {
+                                const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&ra[q][0]);
+                                const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&ra[q][1]);
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    float2 fa = __bfloat1622float2(ha[i]), fb = __bfloat1622float2(hb[i]);
+                                    v[2 * i] += fa.x; v[2 * i + 1] += fa.y; v[8 + 2 * i] += fb.x; v[8 + 2 * i + 1] += fb.y;
+                                }
+                            }
+                            uint4 o0, o1;
+                            __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&o0);
+                            __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&o1);
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
-                                float2 fa = __bfloat1622float2(ha[i]), fb = __bfloat1622float2(hb[i]);
-                                v[2 * i] += fa.x; v[2 * i + 1] += fa.y; v[8 + 2 * i] += fb.x; v[8 + 2 * i + 1] += fb.y;
+                                h0[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                                h1[i] = __floats2bfloat162_rn(v[8 + 2 * i], v[8 + 2 * i + 1]);
+                            }
+                            if (!(p.exp & 8) || o0.x == 0x12345678u) {        // exp bit 3: no global stores (diagnostic)
+                                *reinterpret_cast<uint4*>(orow + c) = o0;
+                                *reinterpret_cast<uint4*>(orow + c + 8) = o1;
                             }
                         }
-                        if (p.accum) {
-                            uint4 a = *reinterpret_cast<const uint4*>(orow + c0), b = *reinterpret_cast<const uint4*>(orow + c0 + 8);
-                            const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
-                            const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&b);
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                float2 fa = __bfloat1622float2(ha[i]), fb = __bfloat1622float2(hb[i]);
-                                v[2 * i] += fa.x; v[2 * i + 1] += fa.y; v[8 + 2 * i] += fb.x; v[8 + 2 * i + 1] += fb.y;
-                            }
-                        }
-                        uint4 o0, o1;
-                        __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&o0);
-                        __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&o1);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            h0[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-                            h1[i] = __floats2bfloat162_rn(v[8 + 2 * i], v[8 + 2 * i + 1]);
-                        }
-                        *reinterpret_cast<uint4*>(orow + c0) = o0;
-                        *reinterpret_cast<uint4*>(orow + c0 + 8) = o1;
                     }
                 }
             }
@@ -735,6 +776,8 @@ static int conv_tc2_launch(const ddpm_conv_args* a, cudaStream_t st) {
     p.Qtot = a->in.N * p.Hp * p.Wp;
     p.accum = (a->epi & DDPM_EPI_ACCUM) ? 1 : 0;
     p.sub = a->stride == 2 ? 1 : 0; p.exp = g_tc_exp;
+    p.vec_bias = a->bias && (((uintptr_t)a->bias & 15) == 0);
+    p.vec_tbias = a->tbias && (((uintptr_t)a->tbias & 15) == 0) && (a->tbias_pitch % 4 == 0);
     int MT = 256 / p.NT; if (MT > 2) MT = 2; if (MT < 1) MT = 1;
     // small problems: prefer more, smaller items so that every SM pair gets one
     if (MT == 2 && (int64_t)ceil_div(p.Qtot, 512) * p.n_tiles < sm_count() / 2) MT = 1;

@@ -18,6 +18,7 @@ ap.add_argument("--only", default="conv,wgrad,gn,colsum,ew,param")
 ap.add_argument("--exp", action="store_true", help="conv: also run with A / B / both TMA loads skipped (diagnostic)")
 ap.add_argument("--reps", type=int, default=10)
 ap.add_argument("--json", default=None)
+ap.add_argument("--epi", action="store_true", help="conv: also time with bias + time-bias + residual epilogue")
 ap.add_argument("--v1", action="store_true", help="conv: also time the first-generation kernel")
 ap.add_argument("--shape", default=None, help="restrict conv/wgrad to one 'Cin,Cout,H' (for ncu)")
 args = ap.parse_args()
@@ -83,12 +84,20 @@ if "conv" in only:
         x = E.act(B, hw, hw, ci); x.interior().normal_()
         y = E.act(B, hw, hw, co)
         fl = 2.0 * B * hw * hw * co * ci * ks * ks
-        modes = [(1, "")] + ([(1 | (1 << 4), " skipA"), (1 | (2 << 4), " skipB"), (1 | (3 << 4), " skipAB")] if args.exp else [])
+        modes = [(1, "")] + ([(1 | (3 << 4), " skipAB"), (1 | (4 << 4), " skipEpi"), (1 | (8 << 4), " skipStores"), (1 | (7 << 4), " skipAB+Epi")] if args.exp else [])
         for mode, tag in modes:
             _lib.lib.ddpm_set_tc_mode(mode, 0)
             sec = timeit(lambda: engine.conv(E, x, wf, y, ks, 1, ks // 2))
             report("conv", f"{ci}->{co}@{hw}k{ks}{tag}", sec, flops=fl, cnt=2 * cnt)
         _lib.lib.ddpm_set_tc_mode(1, 0)
+        if args.epi:
+            bias = torch.randn(co, device=dev); tb = torch.randn(B, co, device=dev)
+            r = E.act(B, hw, hw, co); r.interior().normal_()
+            sec = timeit(lambda: engine.conv(E, x, wf, y, ks, 1, ks // 2, bias=bias, tbias=tb, res=r))
+            report("conv", f"{ci}->{co}@{hw}k{ks} skip(+bias+tbias+res)", sec, flops=fl, cnt=2 * cnt)
+            sec = timeit(lambda: engine.conv(E, x, wf, y, ks, 1, ks // 2, bias=bias, accum=True))
+            report("conv", f"{ci}->{co}@{hw}k{ks} skip(+bias+accum)", sec, flops=fl, cnt=2 * cnt)
+            del r
         if args.v1:
             _lib.lib.ddpm_set_tc_v2(0)
             sec = timeit(lambda: engine.conv(E, x, wf, y, ks, 1, ks // 2))
