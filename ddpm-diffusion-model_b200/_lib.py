@@ -70,6 +70,7 @@ SIGNATURES = {
     "ddpm_gn_apply": [_TP, _i, _i, _vp, _vp, _vp, _f, _i, _f, _vp, _u32, _TP, _vp],
     "ddpm_gn_fwd": [_TP, _i, _i, _vp, _vp, _vp, _f, _i, _f, _vp, _u32, _TP, _vp],
     "ddpm_gn_bwd": [_TP, _i, _i, _vp, _vp, _vp, _f, _i, _f, _vp, _u32, _TP, _TP, _i, _vp, _vp, _vp, _vp],
+    "ddpm_gn_bwd_colsum": [_TP, _i, _i, _vp, _vp, _vp, _f, _i, _f, _vp, _u32, _TP, _TP, _i, _vp, _vp, _vp, _vp, _i, _vp],
     "ddpm_upsample2x": [_TP, _TP, _i, _vp],
     "ddpm_upsample2x_bwd": [_TP, _TP, _i, _i, _vp],
     "ddpm_zero_upsample2x": [_TP, _TP, _i, _vp],

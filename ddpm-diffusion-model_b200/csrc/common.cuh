@@ -152,24 +152,39 @@ __device__ __forceinline__ uint32_t dropout_mask(const uint64_t* rng, uint32_t l
     }
     return m;
 }
-// Dropout keep-bits from 16-bit words: ONE Philox call per 8 consecutive elements (e0 % VEC == 0, VEC in
-// {1, 4, 8}); element e uses 16-bit word (e & 7) of the call with counter e >> 3, so the fp32 (VEC 4), bf16
-// (VEC 8) and scalar paths draw the same mask.  keep iff word >= thr16 = round(p * 65536).
-template <int VEC>
-__device__ __forceinline__ uint32_t dropout_mask16(const uint64_t* rng, uint32_t layer, uint64_t e0, uint32_t thr16) {
+// Dropout keep-bits.  The GroupNorm kernels are instruction-bound on B200 (an SM has ~22 B/clk of HBM
+// bandwidth, i.e. a budget of ~20 instructions per bf16 element), and Philox4x32-10 cost ~12 of them.
+// Parity with ATen's mask is statistical only, so the mask comes from a counter hash:
+// element e uses 16-bit half (e & 1) of lowbias32((e >> 1) ^ key), key = f(seed, step, layer); keep iff
+// half >= thr16 = round(p * 65536).  ~4 instructions per element; fp32 (VEC 4), bf16 (VEC 8) and scalar paths
+// draw the same mask; forward and backward recompute it from the same (seed, step, layer, index).
+__device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ uint32_t dropout_key(const uint64_t* rng, uint32_t layer) {
     const uint64_t seed = rng[0], step = rng[1];
-    const uint64_t e = e0 >> 3;
-    const uint4 r = philox4((uint32_t)seed, (uint32_t)(seed >> 32),
-                            make_uint4((uint32_t)e, (uint32_t)(e >> 32), (uint32_t)step, layer));
-    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+    uint32_t k = lowbias32((uint32_t)seed ^ 0x9E3779B9U);
+    k = lowbias32(k ^ (uint32_t)(seed >> 32));
+    k = lowbias32(k + (uint32_t)step * 0x85EBCA6BU);
+    k = lowbias32(k ^ (layer * 0xC2B2AE35U));
+    return k;
+}
+template <int VEC>
+__device__ __forceinline__ uint32_t dropout_mask16(uint32_t key, uint64_t e0, uint32_t thr16) {
+    const uint32_t base = ((uint32_t)(e0 >> 1) ^ ((uint32_t)(e0 >> 33) * 0x9E3779B9U)) ^ key;
     uint32_t m = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const uint32_t h = (w[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
-        m |= (h >= thr16 ? 1u : 0u) << i;
+    if (VEC == 1) {
+        const uint32_t h = lowbias32(base);
+        return (((e0 & 1) ? (h >> 16) : (h & 0xffffu)) >= thr16) ? 1u : 0u;
     }
-    if (VEC == 8) return m;
-    return (m >> (uint32_t)(e0 & 7)) & ((1u << VEC) - 1u);
+#pragma unroll
+    for (int i = 0; i < VEC / 2; ++i) {
+        const uint32_t h = lowbias32(base + (uint32_t)i);      // (e0 >> 1) + i: VEC consecutive elements, e0 % VEC == 0
+        m |= ((h & 0xffffu) >= thr16 ? 1u : 0u) << (2 * i);
+        m |= ((h >> 16) >= thr16 ? 1u : 0u) << (2 * i + 1);
+    }
+    return m;
 }
 // keep-mask for element index `e` (one Philox call covers 4 consecutive elements)
 __device__ __forceinline__ bool dropout_keep(const uint64_t* rng, uint32_t layer, uint64_t e, float p) {

@@ -98,7 +98,10 @@ struct GnP {
     const float* gamma; const float* beta;
     double* stats;               // [N][G][2] (sum, sum of squares)
     float* dgamma; float* dbeta; // backward: accumulated with atomics (may be NULL)
+    float* cs_nc; float* cs_c;   // backward: per-image / total channel sums of the final dx (conv bias and time-bias gradients)
     int accumulate;              // backward: dx += ...
+    int stash;                   // backward: dy may be overwritten -> phase 1 leaves dz there, phase 2 skips mask / act'
+
     int wshift;                  // log2(W) when W is a power of two, else -1
 };
 
@@ -141,6 +144,7 @@ __global__ void __launch_bounds__(NT, 3) gn_fwd_kernel(GnP a) {
     const int per = (HW + CS - 1) / CS;
     const int p0 = rank * per, p1 = min(HW, p0 + per);
     const int c0 = m.cv * VEC;
+    const uint32_t dkey = a.thr16 ? dropout_key(a.rng, a.layer) : 0u;
     constexpr int U = 8;
 
     if (MODE != 2) {
@@ -219,7 +223,7 @@ __global__ void __launch_bounds__(NT, 3) gn_fwd_kernel(GnP a) {
                     float v[VEC];
                     unraw<T, VEC>(r[u], v);
                     uint32_t keep = 0xffffffffu;
-                    if (a.thr16) keep = dropout_mask16<VEC>(a.rng, a.layer, ((uint64_t)n * HW + p) * C + c0, a.thr16);
+                    if (a.thr16) keep = dropout_mask16<VEC>(dkey, ((uint64_t)n * HW + p) * C + c0, a.thr16);
 #pragma unroll
                     for (int i = 0; i < VEC; ++i) {
                         float z = fmaf(v[i], sc[i], sh[i]);
@@ -256,6 +260,7 @@ __global__ void __launch_bounds__(NT, 2) gn_bwd_kernel(GnP a) {
     const int per = (HW + CS - 1) / CS;
     const int p0 = rank * per, p1 = min(HW, p0 + per);
     const int c0 = m.cv * VEC;
+    const uint32_t dkey = a.thr16 ? dropout_key(a.rng, a.layer) : 0u;
     constexpr int U = 4;
 
     for (int g = threadIdx.x; g < G; g += NT) {
@@ -296,14 +301,16 @@ __global__ void __launch_bounds__(NT, 2) gn_bwd_kernel(GnP a) {
                         float v[VEC], d[VEC];
                         unraw<T, VEC>(rx[u], v); unraw<T, VEC>(rd[u], d);
                         uint32_t keep = 0xffffffffu;
-                        if (a.thr16) keep = dropout_mask16<VEC>(a.rng, a.layer, ((uint64_t)n * HW + p) * C + c0, a.thr16);
+                        if (a.thr16) keep = dropout_mask16<VEC>(dkey, ((uint64_t)n * HW + p) * C + c0, a.thr16);
 #pragma unroll
                         for (int i = 0; i < VEC; ++i) {
                             const float xh = fmaf(v[i], rs[i], -mr[i]);
                             float dz = ((keep >> i) & 1u) ? d[i] * a.keep_scale : 0.f;
                             if (a.act) dz *= dsilu_f(fmaf(xh, ga[i], be[i]));
                             acc[i] += dz; acc[VEC + i] = fmaf(dz, xh, acc[VEC + i]);
+                            d[i] = dz;
                         }
+                        if (a.stash) { int y, xx; split_pix(p, W, a.wshift, y, xx); stv<T, VEC>(a.dy.at<T>(n, y, xx, c0), d); }
                     }
                 }
             }
@@ -335,6 +342,9 @@ __global__ void __launch_bounds__(NT, 2) gn_bwd_kernel(GnP a) {
     __syncthreads();
 
     // ---- phase 2: dx (x and dy are L2 hits now)
+    float csum[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) csum[i] = 0.f;
     if (m.active) {
         float ra[VEC], rb[VEC];
 #pragma unroll
@@ -362,14 +372,19 @@ __global__ void __launch_bounds__(NT, 2) gn_bwd_kernel(GnP a) {
                     unraw<T, VEC>(rx[u], v); unraw<T, VEC>(rd[u], d);
                     if (a.accumulate) unraw<T, VEC>(ro[u], r);
                     uint32_t keep = 0xffffffffu;
-                    if (a.thr16) keep = dropout_mask16<VEC>(a.rng, a.layer, ((uint64_t)n * HW + p) * C + c0, a.thr16);
+                    if (a.thr16 && !a.stash) keep = dropout_mask16<VEC>(dkey, ((uint64_t)n * HW + p) * C + c0, a.thr16);
 #pragma unroll
                     for (int i = 0; i < VEC; ++i) {
                         const float xh = fmaf(v[i], rs[i], -mr[i]);
-                        float dz = ((keep >> i) & 1u) ? d[i] * a.keep_scale : 0.f;
-                        if (a.act) dz *= dsilu_f(fmaf(xh, ga[i], be[i]));
+                        float dz = d[i];                                   // already dz when phase 1 stashed it
+                        if (!a.stash) {
+                            dz = ((keep >> i) & 1u) ? d[i] * a.keep_scale : 0.f;
+                            if (a.act) dz *= dsilu_f(fmaf(xh, ga[i], be[i]));
+                        }
                         const float g = fmaf(dz * ga[i], rs[i], -ra[i]) - xh * rb[i];     // rs*(dz*ga - A - xh*B)
                         r[i] = a.accumulate ? r[i] + g : g;
+                        if (sizeof(T) == 2) r[i] = __bfloat162float(__float2bfloat16_rn(r[i]));   // what is stored is what is summed
+                        csum[i] += r[i];
                     }
                     int y, xx; split_pix(p, W, a.wshift, y, xx);
                     stv<T, VEC>(a.o.at<T>(n, y, xx, c0), r);
@@ -377,7 +392,17 @@ __global__ void __launch_bounds__(NT, 2) gn_bwd_kernel(GnP a) {
             }
         }
     }
-    cluster_wait();
+    cluster_wait();                                          // peers are done with chan[] -> it can be reused
+    if (a.cs_nc || a.cs_c) {
+        // fused column sums of dx: the bias gradient of the convolution that produced x and the
+        // per-image time-bias gradient (replaces a separate pass over dx, ddpm_colsum)
+        cta_channel_reduce<VEC, 1>(part, csum, chan, C, m);
+        for (int c = threadIdx.x; c < C; c += NT) {
+            const float v = (float)chan[c];
+            if (a.cs_nc) atomicAdd(a.cs_nc + (size_t)n * C + c, v);
+            if (a.cs_c) atomicAdd(a.cs_c + c, v);
+        }
+    }
 }
 
 // cluster size: enough CTAs per image that a thread sees ~16 packets per phase, at most 8 (portable limit)
@@ -411,7 +436,7 @@ static int gn_fill(GnP& p, const ddpm_tensor* x, int groups, const double* stats
     p.thr16 = p_drop > 0.f ? (uint32_t)(p_drop * 65536.0f + 0.5f) : 0u;
     p.keep_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
     p.rng = rng; p.layer = layer; p.gamma = gamma; p.beta = beta; p.stats = const_cast<double*>(stats);
-    p.dgamma = p.dbeta = nullptr; p.accumulate = 0; p.wshift = log2_exact(x->W);
+    p.dgamma = p.dbeta = nullptr; p.cs_nc = p.cs_c = nullptr; p.accumulate = 0; p.stash = 0; p.wshift = log2_exact(x->W);
     return 0;
 }
 
@@ -458,17 +483,18 @@ extern "C" int ddpm_gn_fwd(const ddpm_tensor* x, int dtype, int groups, double* 
     return gn_fwd_dispatch<0>(p, x, out, dtype, (cudaStream_t)stream);
 }
 
-extern "C" int ddpm_gn_bwd(const ddpm_tensor* x, int dtype, int groups, const double* stats, const float* gamma,
-                           const float* beta, float eps, int act, float p_drop, const uint64_t* rng,
-                           uint32_t layer_id, const ddpm_tensor* dy, const ddpm_tensor* dx, int accumulate,
-                           float* dgamma, float* dbeta, float* ws, void* stream) {
-    (void)ws;                                  // kept in the signature for ABI stability; no longer needed
+static int gn_bwd_impl(const ddpm_tensor* x, int dtype, int groups, const double* stats, const float* gamma,
+                       const float* beta, float eps, int act, float p_drop, const uint64_t* rng,
+                       uint32_t layer_id, const ddpm_tensor* dy, const ddpm_tensor* dx, int accumulate,
+                       float* dgamma, float* dbeta, float* cs_nc, float* cs_c, int dy_scratch, void* stream) {
     if (!tensor_ok(x) || !tensor_ok(dy) || !tensor_ok(dx) || !stats || !gamma || !beta) return DDPM_E_ARG;
     if (groups <= 0 || x->C % groups || dy->C != x->C || dx->C != x->C) return DDPM_E_ARG;
     if (dy->N != x->N || dy->H != x->H || dy->W != x->W || dx->N != x->N || dx->H != x->H || dx->W != x->W) return DDPM_E_ARG;
     GnP p; int rc = gn_fill(p, x, groups, stats, gamma, beta, eps, act, p_drop, rng, layer_id); if (rc) return rc;
     p.dy = TV(*dy); p.o = TV(*dx); p.accumulate = accumulate; p.dgamma = dgamma; p.dbeta = dbeta;
+    p.cs_nc = cs_nc; p.cs_c = cs_c; p.stash = dy_scratch ? 1 : 0;
     cudaStream_t st = (cudaStream_t)stream;
+    if (cs_nc) CUDA_TRY(cudaMemsetAsync(cs_nc, 0, sizeof(float) * x->N * x->C, st));
     const int HW = x->H * x->W, C = x->C;
     const size_t sm = sizeof(double) * 2 * C + sizeof(float) * (2 * C + 4 * groups);
 #define GO(T, VEC) { int cvs = C / VEC; if (cvs > NT) return DDPM_E_ARG; int cs = gn_cluster_size(HW, cvs); \
@@ -477,6 +503,23 @@ extern "C" int ddpm_gn_bwd(const ddpm_tensor* x, int dtype, int groups, const do
     else if (dtype == DDPM_F32) { if (vec_ok(x, 4, 4) && vec_ok(dy, 4, 4) && vec_ok(dx, 4, 4)) GO(float, 4) else GO(float, 1) }
 #undef GO
     return DDPM_E_ARG;
+}
+
+extern "C" int ddpm_gn_bwd(const ddpm_tensor* x, int dtype, int groups, const double* stats, const float* gamma,
+                           const float* beta, float eps, int act, float p_drop, const uint64_t* rng,
+                           uint32_t layer_id, const ddpm_tensor* dy, const ddpm_tensor* dx, int accumulate,
+                           float* dgamma, float* dbeta, float* ws, void* stream) {
+    (void)ws;                                  // kept in the signature for ABI stability; no longer needed
+    return gn_bwd_impl(x, dtype, groups, stats, gamma, beta, eps, act, p_drop, rng, layer_id, dy, dx, accumulate,
+                       dgamma, dbeta, nullptr, nullptr, 0, stream);
+}
+
+extern "C" int ddpm_gn_bwd_colsum(const ddpm_tensor* x, int dtype, int groups, const double* stats, const float* gamma,
+                                  const float* beta, float eps, int act, float p_drop, const uint64_t* rng,
+                                  uint32_t layer_id, const ddpm_tensor* dy, const ddpm_tensor* dx, int accumulate,
+                                  float* dgamma, float* dbeta, float* colsum_nc, float* colsum_c, int dy_scratch, void* stream) {
+    return gn_bwd_impl(x, dtype, groups, stats, gamma, beta, eps, act, p_drop, rng, layer_id, dy, dx, accumulate,
+                       dgamma, dbeta, colsum_nc, colsum_c, dy_scratch, stream);
 }
 
 // ------------------------------------------------------------------------------------ pixel maps

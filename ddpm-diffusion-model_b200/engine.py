@@ -311,11 +311,16 @@ def gn_fwd(E: Exec, x: Act, gn: torch.nn.GroupNorm, act: int, p_drop: float, lay
 
 
 def gn_bwd(E: Exec, x: Act, st: torch.Tensor, gn: torch.nn.GroupNorm, act: int, p_drop: float, layer: int,
-           dy: Act, dx: Act, accumulate: bool) -> Act:
-    _lib.call("ddpm_gn_bwd", C.byref(x.desc()), x.dt, gn.num_groups, st.data_ptr(), gn.weight.data_ptr(),
+           dy: Act, dx: Act, accumulate: bool, colsum_nc: Optional[torch.Tensor] = None,
+           colsum_bias: Optional[torch.nn.Parameter] = None, dy_scratch: bool = False) -> Act:
+    """`colsum_nc` ([N][C] fp32, overwritten) / `colsum_bias` (parameter whose .grad is accumulated) receive the
+    channel sums of the final dx from the same launch.  `dy_scratch`: dy is dead after this call (true for every
+    gradient temporary of the UNet backward) -> the kernel may overwrite it (see ddpm_gn_bwd_colsum)."""
+    _lib.call("ddpm_gn_bwd_colsum", C.byref(x.desc()), x.dt, gn.num_groups, st.data_ptr(), gn.weight.data_ptr(),
               gn.bias.data_ptr(), float(gn.eps), act, float(p_drop), E.rng.data_ptr() if p_drop > 0 else None,
               layer, C.byref(dy.desc()), C.byref(dx.desc()), 1 if accumulate else 0, _gptr(gn.weight),
-              _gptr(gn.bias), None, E.stream)
+              _gptr(gn.bias), colsum_nc.data_ptr() if colsum_nc is not None else None, _gptr(colsum_bias),
+              1 if dy_scratch else 0, E.stream)
     return dx
 
 
@@ -409,9 +414,10 @@ def resblock_bwd(E: Exec, blk, saved, dout: Act, dx: Optional[Act] = None, dx_ac
     colsum(E, dout, None, blk.conv2.bias)
     _, w2d = E.wcache.get(E, blk.conv2.weight, E.dt, True)
     da2 = conv(E, dout, w2d, E.act(x.N, x.H, x.W, blk.out_ch), 3, 1, 1)
-    dh = gn_bwd(E, h, st2, blk.norm2, 1, p_drop, layer, da2, da2, False)        # in place: dh overwrites da2
     dtb = E.f32(x.N, blk.out_ch)
-    colsum(E, dh, dtb, blk.conv1.bias)
+    # in place (dh overwrites da2); the same launch emits d(time bias) and d(conv1.bias)
+    dh = gn_bwd(E, h, st2, blk.norm2, 1, p_drop, layer, da2, da2, False, colsum_nc=dtb, colsum_bias=blk.conv1.bias,
+                dy_scratch=True)
     wgrad(E, a1, dh, blk.conv1.weight, 3, 1, 1)
     _, w1d = E.wcache.get(E, blk.conv1.weight, E.dt, True)
     da1 = conv(E, dh, w1d, E.act(x.N, x.H, x.W, blk.in_ch), 3, 1, 1)
@@ -422,12 +428,12 @@ def resblock_bwd(E: Exec, blk, saved, dout: Act, dx: Optional[Act] = None, dx_ac
         if dx is None:
             dx, dx_accum = E.act(x.N, x.H, x.W, blk.in_ch), False
         conv(E, dout, wsd, dx, 1, accum=dx_accum)
-        gn_bwd(E, x, st1, blk.norm1, 1, 0.0, 0, da1, dx, True)
+        gn_bwd(E, x, st1, blk.norm1, 1, 0.0, 0, da1, dx, True, dy_scratch=True)
     else:
         if dx is None:
-            dx = gn_bwd(E, x, st1, blk.norm1, 1, 0.0, 0, da1, dout, True)       # dout += gn_bwd -> dx
+            dx = gn_bwd(E, x, st1, blk.norm1, 1, 0.0, 0, da1, dout, True, dy_scratch=True)       # dout += gn_bwd -> dx
         else:
-            gn_bwd(E, x, st1, blk.norm1, 1, 0.0, 0, da1, dx, dx_accum)
+            gn_bwd(E, x, st1, blk.norm1, 1, 0.0, 0, da1, dx, dx_accum, dy_scratch=True)
             add(E, dx, dout, dx)
     return dx, dtb
 
@@ -469,8 +475,8 @@ def attn_bwd(E: Exec, blk, saved, dout: Act, dx: Optional[Act] = None, dx_accum:
     _, wqd = E.wcache.get(E, blk.qkv.weight, E.dt, True)
     da = conv(E, dqkv, wqd, E.act(x.N, x.H, x.W, x.C), 1)
     if dx is None:
-        return gn_bwd(E, x, st, blk.norm, 0, 0.0, 0, da, dout, True)
-    gn_bwd(E, x, st, blk.norm, 0, 0.0, 0, da, dx, dx_accum)
+        return gn_bwd(E, x, st, blk.norm, 0, 0.0, 0, da, dout, True, dy_scratch=True)
+    gn_bwd(E, x, st, blk.norm, 0, 0.0, 0, da, dx, dx_accum, dy_scratch=True)
     return add(E, dx, dout, dx)
 
 
@@ -703,7 +709,7 @@ def unet_backward(E: Exec, model, saved, dy: torch.Tensor, need_dx: bool, progre
     colsum(E, dyn.slice(0, oc) if dyn.C != oc else dyn, None, model.out_conv.bias)
     _, wd = E.wcache.get(E, model.out_conv.weight, E.dt, True, cout_pad=cpad)
     da = conv(E, dyn, wd, E.act(a.N, a.H, a.W, a.C), 3, 1, 1)
-    dcur = gn_bwd(E, cur_h, st, model.out_norm, 1, 0.0, 0, da, da, False)
+    dcur = gn_bwd(E, cur_h, st, model.out_norm, 1, 0.0, 0, da, da, False, dy_scratch=True)
     del da, dyn
     if progress is not None:
         progress(model.out_conv)

@@ -112,6 +112,16 @@ int ddpm_gn_bwd(const ddpm_tensor* x, int dtype, int groups, const double* stats
                 uint32_t layer_id, const ddpm_tensor* dy, const ddpm_tensor* dx, int accumulate,
                 float* dgamma, float* dbeta, float* ws, void* stream);
 
+/* ddpm_gn_bwd that also emits the channel sums of the final dx: colsum_nc[n][c] (fp32, overwritten; may
+ * be NULL) and colsum_c[c] += sum_n (may be NULL) -- the time-bias / conv-bias gradients of the layer that
+ * produced x (unet_backbone.py:41,22), saving a separate ddpm_colsum pass over dx.
+ * dy_scratch != 0: the caller no longer needs dy; the reduction phase leaves dz = dy*mask*act'(z) in it so
+ * the second phase skips the mask / activation-derivative recomputation (dy's contents are then undefined). */
+int ddpm_gn_bwd_colsum(const ddpm_tensor* x, int dtype, int groups, const double* stats, const float* gamma,
+                       const float* beta, float eps, int act, float p_drop, const uint64_t* rng,
+                       uint32_t layer_id, const ddpm_tensor* dy, const ddpm_tensor* dx, int accumulate,
+                       float* dgamma, float* dbeta, float* colsum_nc, float* colsum_c, int dy_scratch, void* stream);
+
 /* nearest x2 (unet_backbone.py:63) and its adjoint (2x2 sum) */
 int ddpm_upsample2x(const ddpm_tensor* x, const ddpm_tensor* out, int dtype, void* stream);
 int ddpm_upsample2x_bwd(const ddpm_tensor* dy, const ddpm_tensor* dx, int dtype, int accumulate, void* stream);

@@ -245,6 +245,20 @@ def test_groupnorm_fwd_bwd(pkg, shape, act, dt_name):
     assert rel(_from_act(pkg, E, dxa), xr.grad) < tol
     assert rel(gdev.weight.grad, gn.weight.grad) < tol
     assert rel(gdev.bias.grad, gn.bias.grad) < tol
+    # scratch-dy variant with fused column sums (what the UNet backward uses)
+    gdev.weight.grad = None; gdev.bias.grad = None
+    dyb = _to_act(pkg, E, dy)
+    cs_nc = torch.full((N, Cc), 7.0, device=dev())
+    cbias = torch.nn.Parameter(torch.zeros(Cc, device=dev()))
+    dxb = engine.gn_bwd(E, xa, st, gdev, act, 0.0, 0, dyb, E.act(N, H, W, Cc), False, colsum_nc=cs_nc, colsum_bias=cbias,
+                        dy_scratch=True)
+    got = _from_act(pkg, E, dxb)
+    assert rel(got, xr.grad) < tol
+    assert rel(gdev.weight.grad, gn.weight.grad) < tol
+    # (per-group sums of a GroupNorm gradient are ~0, so compare against the scale of sum|dx|, not of the sum)
+    ctol = 1e-5 if dt_name == "f32" else 2e-3
+    assert float((cs_nc.cpu() - got.sum((2, 3))).abs().max()) < ctol * float(got.abs().sum((2, 3)).max())
+    assert float((cbias.grad.cpu() - got.sum((0, 2, 3))).abs().max()) < ctol * float(got.abs().sum((0, 2, 3)).max())
     # accumulate variant: dx += ...
     base = torch.randn(N, Cc, H, W)
     if dt_name == "bf16":
