@@ -70,11 +70,16 @@ template <> struct Vec16<bf16> {
     }
 };
 
-// SiLU via ex2.approx + rcp.approx (2 MUFU per element; ~2 ulp, far inside the 1e-4 fp32 parity budget)
-__device__ __forceinline__ float silu_f(float z) { return __fdividef(z, 1.0f + __expf(-z)); }
+// SiLU via ex2.approx + rcp.approx: 2 MUFU + 3 FP32 instructions per element (~2 ulp, far inside the 1e-4
+// fp32 parity budget).  __expf / __fdividef expand to range-checked sequences (FSETP/FSEL/extra FMULs) that
+// doubled the instruction count of the GroupNorm kernels, which are issue-bound on B200.
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigmoid_f(float z) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * z)); }
+__device__ __forceinline__ float silu_f(float z) { return z * sigmoid_f(z); }
 __device__ __forceinline__ float dsilu_f(float z) {
-    float s = __fdividef(1.0f, 1.0f + __expf(-z));
-    return s * fmaf(z, 1.0f - s, 1.0f);
+    const float s = sigmoid_f(z);
+    return fmaf(z * (1.0f - s), s, s);          // s * (1 + z (1 - s))
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -169,6 +174,22 @@ __device__ __forceinline__ uint32_t dropout_key(const uint64_t* rng, uint32_t la
     k = lowbias32(k + (uint32_t)step * 0x85EBCA6BU);
     k = lowbias32(k ^ (layer * 0xC2B2AE35U));
     return k;
+}
+// in-place: v[i] = keep_i ? v[i] * scale : 0 for the VEC elements starting at (wrapping 32-bit) index e0
+template <int VEC>
+__device__ __forceinline__ void dropout_apply(float* v, uint32_t key, uint32_t e0, uint32_t thr16, float scale) {
+    const uint32_t base = (e0 >> 1) ^ key;
+    if (VEC == 1) {
+        const uint32_t h = lowbias32(base);
+        v[0] = (((e0 & 1) ? (h >> 16) : (h & 0xffffu)) >= thr16) ? v[0] * scale : 0.f;
+        return;
+    }
+#pragma unroll
+    for (int i = 0; i < VEC / 2; ++i) {
+        const uint32_t h = lowbias32(base + (uint32_t)i);
+        v[2 * i] = ((h & 0xffffu) >= thr16) ? v[2 * i] * scale : 0.f;
+        v[2 * i + 1] = ((h >> 16) >= thr16) ? v[2 * i + 1] * scale : 0.f;
+    }
 }
 template <int VEC>
 __device__ __forceinline__ uint32_t dropout_mask16(uint32_t key, uint64_t e0, uint32_t thr16) {

@@ -105,6 +105,23 @@ struct GnP {
     int wshift;                  // log2(W) when W is a power of two, else -1
 };
 
+// interior pixel index p = y*W + x  ->  padded-linear pixel index of a view (3 integer instructions when W is
+// a power of two); the element offset from the image's padded origin is q * pitch
+struct PixAddr {
+    int ws, W, Wp, h2, q0, pitch;
+    __device__ __forceinline__ PixAddr(const TV& t, int wshift)
+        : ws(wshift), W(t.W), Wp(t.Wp), h2(2 * t.halo), q0(t.halo * t.Wp + t.halo), pitch(t.pitch) {}
+    __device__ __forceinline__ int q(int p) const {
+        if (ws >= 0) return p + h2 * (p >> ws) + q0;
+        const int y = p / W;
+        return y * Wp + (p - y * W) + q0;
+    }
+    template <typename T> __device__ __forceinline__ T* at(T* img, int p) const { return img + (int64_t)q(p) * pitch; }
+};
+template <typename T> __device__ __forceinline__ T* img_origin(const TV& t, int n, int c0) {
+    return reinterpret_cast<T*>(t.ptr) + (int64_t)n * t.Hp * t.Wp * t.pitch + c0;
+}
+
 __device__ __forceinline__ void split_pix(int p, int W, int wshift, int& y, int& x) {
     if (wshift >= 0) { y = p >> wshift; x = p & (W - 1); }
     else { y = p / W; x = p - y * W; }
@@ -145,7 +162,11 @@ __global__ void __launch_bounds__(NT, 3) gn_fwd_kernel(GnP a) {
     const int p0 = rank * per, p1 = min(HW, p0 + per);
     const int c0 = m.cv * VEC;
     const uint32_t dkey = a.thr16 ? dropout_key(a.rng, a.layer) : 0u;
-    constexpr int U = 8;
+    const uint32_t ebase = (uint32_t)n * (uint32_t)HW * (uint32_t)C + (uint32_t)c0;   // wrapping element index (mask hash input)
+    const PixAddr ax(a.x, a.wshift), ao(a.o, a.wshift);
+    const T* xb = img_origin<T>(a.x, n, c0);
+    T* ob = img_origin<T>(a.o, n, c0);
+    constexpr int U = 4;
 
     if (MODE != 2) {
         float acc[2 * VEC];
@@ -157,7 +178,7 @@ __global__ void __launch_bounds__(NT, 3) gn_fwd_kernel(GnP a) {
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const int p = pb + u * m.ppi;
-                    if (p < p1) { int y, xx; split_pix(p, W, a.wshift, y, xx); ldraw<T, VEC>(a.x.at<T>(n, y, xx, c0), r[u]); }
+                    if (p < p1) ldraw<T, VEC>(ax.at(xb, p), r[u]);
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
@@ -214,7 +235,7 @@ __global__ void __launch_bounds__(NT, 3) gn_fwd_kernel(GnP a) {
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int p = pb + u * m.ppi;
-                if (p < p1) { int y, xx; split_pix(p, W, a.wshift, y, xx); ldraw<T, VEC>(a.x.at<T>(n, y, xx, c0), r[u]); }
+                if (p < p1) ldraw<T, VEC>(ax.at(xb, p), r[u]);
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -222,16 +243,13 @@ __global__ void __launch_bounds__(NT, 3) gn_fwd_kernel(GnP a) {
                 if (p < p1) {
                     float v[VEC];
                     unraw<T, VEC>(r[u], v);
-                    uint32_t keep = 0xffffffffu;
-                    if (a.thr16) keep = dropout_mask16<VEC>(dkey, ((uint64_t)n * HW + p) * C + c0, a.thr16);
 #pragma unroll
                     for (int i = 0; i < VEC; ++i) {
-                        float z = fmaf(v[i], sc[i], sh[i]);
-                        if (a.act) z = silu_f(z);
-                        v[i] = ((keep >> i) & 1u) ? z * a.keep_scale : 0.f;
+                        const float z = fmaf(v[i], sc[i], sh[i]);
+                        v[i] = a.act ? silu_f(z) : z;
                     }
-                    int y, xx; split_pix(p, W, a.wshift, y, xx);
-                    stv<T, VEC>(a.o.at<T>(n, y, xx, c0), v);
+                    if (a.thr16) dropout_apply<VEC>(v, dkey, ebase + (uint32_t)p * (uint32_t)C, a.thr16, a.keep_scale);
+                    stv<T, VEC>(ao.at(ob, p), v);
                 }
             }
         }
@@ -242,10 +260,10 @@ __global__ void __launch_bounds__(NT, 3) gn_fwd_kernel(GnP a) {
 // backward: z = x*sc+sh, y = drop(act(z)); dz = dy * mask/(1-p) * act'(z)
 //   S1[c] = sum_p dz, S2[c] = sum_p dz*xhat;  A_g = mean_g(gamma*S1), B_g = mean_g(gamma*S2)
 //   dx = rstd * (dz*gamma - A_g - xhat*B_g);  dbeta += S1, dgamma += S2
-template <typename T, int VEC>
-__global__ void __launch_bounds__(NT, 2) gn_bwd_kernel(GnP a) {
+template <typename T, int VEC, bool STASH>
+__global__ void __launch_bounds__(NT, STASH ? 3 : 2) gn_bwd_kernel(GnP a) {
     extern __shared__ __align__(16) unsigned char gsm[];
-    const int C = a.x.C, G = a.G, cpg = C / G, HW = a.x.H * a.x.W, W = a.x.W;
+    const int C = a.x.C, G = a.G, cpg = C / G, HW = a.x.H * a.x.W;
     double* chan = reinterpret_cast<double*>(gsm);           // [2][C] this CTA's per-channel partials (read by peers)
     float* tot = reinterpret_cast<float*>(chan + 2 * C);     // [2][C] cluster totals
     float* gA = tot + 2 * C;                                 // [G]
@@ -261,7 +279,12 @@ __global__ void __launch_bounds__(NT, 2) gn_bwd_kernel(GnP a) {
     const int p0 = rank * per, p1 = min(HW, p0 + per);
     const int c0 = m.cv * VEC;
     const uint32_t dkey = a.thr16 ? dropout_key(a.rng, a.layer) : 0u;
-    constexpr int U = 4;
+    const uint32_t ebase = (uint32_t)n * (uint32_t)HW * (uint32_t)C + (uint32_t)c0;
+    const PixAddr ax(a.x, a.wshift), ad(a.dy, a.wshift), ao(a.o, a.wshift);
+    const T* xb = img_origin<T>(a.x, n, c0);
+    T* db = img_origin<T>(a.dy, n, c0);
+    T* ob = img_origin<T>(a.o, n, c0);
+    constexpr int U = 2;
 
     for (int g = threadIdx.x; g < G; g += NT) {
         const double s = a.stats[((size_t)n * G + g) * 2], q = a.stats[((size_t)n * G + g) * 2 + 1];
@@ -270,15 +293,17 @@ __global__ void __launch_bounds__(NT, 2) gn_bwd_kernel(GnP a) {
         gm[g] = (float)mu; gr[g] = (float)(1.0 / sqrt(var + (double)a.eps));
     }
     __syncthreads();
-    float rs[VEC], mr[VEC], ga[VEC], be[VEC];
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-        const int c = min(c0 + i, C - 1), g = c / cpg;
-        rs[i] = gr[g]; mr[i] = gm[g] * gr[g]; ga[i] = __ldg(a.gamma + c); be[i] = __ldg(a.beta + c);
-    }
 
-    // ---- phase 1: per-channel sums
+    // ---- phase 1: per-channel sums S1 = sum dz, S2 = sum dz*xhat (dz = dy * mask/(1-p) * act'(z))
     {
+        // z = x*sc + sh.  The second moment is accumulated against x, not xhat (two fewer constants and one fewer
+        // FMA per element); S2 = rstd * sum(dz*x) - mean*rstd * sum(dz) is formed from the double-precision totals.
+        float sc[VEC], sh[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            const int c = min(c0 + i, C - 1), g = c / cpg;
+            sc[i] = gr[g] * __ldg(a.gamma + c); sh[i] = __ldg(a.beta + c) - gm[g] * sc[i];
+        }
         float acc[2 * VEC];
 #pragma unroll
         for (int i = 0; i < 2 * VEC; ++i) acc[i] = 0.f;
@@ -288,11 +313,7 @@ __global__ void __launch_bounds__(NT, 2) gn_bwd_kernel(GnP a) {
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const int p = pb + u * m.ppi;
-                    if (p < p1) {
-                        int y, xx; split_pix(p, W, a.wshift, y, xx);
-                        ldraw<T, VEC>(a.x.at<T>(n, y, xx, c0), rx[u]);
-                        ldraw<T, VEC>(a.dy.at<T>(n, y, xx, c0), rd[u]);
-                    }
+                    if (p < p1) { ldraw<T, VEC>(ax.at(xb, p), rx[u]); ldraw<T, VEC>(ad.at(db, p), rd[u]); }
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
@@ -300,17 +321,15 @@ __global__ void __launch_bounds__(NT, 2) gn_bwd_kernel(GnP a) {
                     if (p < p1) {
                         float v[VEC], d[VEC];
                         unraw<T, VEC>(rx[u], v); unraw<T, VEC>(rd[u], d);
-                        uint32_t keep = 0xffffffffu;
-                        if (a.thr16) keep = dropout_mask16<VEC>(dkey, ((uint64_t)n * HW + p) * C + c0, a.thr16);
+                        if (a.thr16) dropout_apply<VEC>(d, dkey, ebase + (uint32_t)p * (uint32_t)C, a.thr16, a.keep_scale);
 #pragma unroll
                         for (int i = 0; i < VEC; ++i) {
-                            const float xh = fmaf(v[i], rs[i], -mr[i]);
-                            float dz = ((keep >> i) & 1u) ? d[i] * a.keep_scale : 0.f;
-                            if (a.act) dz *= dsilu_f(fmaf(xh, ga[i], be[i]));
-                            acc[i] += dz; acc[VEC + i] = fmaf(dz, xh, acc[VEC + i]);
+                            float dz = d[i];
+                            if (a.act) dz *= dsilu_f(fmaf(v[i], sc[i], sh[i]));
+                            acc[i] += dz; acc[VEC + i] = fmaf(dz, v[i], acc[VEC + i]);
                             d[i] = dz;
                         }
-                        if (a.stash) { int y, xx; split_pix(p, W, a.wshift, y, xx); stv<T, VEC>(a.dy.at<T>(n, y, xx, c0), d); }
+                        if (STASH) stv<T, VEC>(ad.at(db, p), d);
                     }
                 }
             }
@@ -318,13 +337,15 @@ __global__ void __launch_bounds__(NT, 2) gn_bwd_kernel(GnP a) {
         cta_channel_reduce<VEC, 2>(part, acc, chan, C, m);
     }
     cluster_arrive(); cluster_wait();                        // every CTA's chan[] is complete
-    for (int o = threadIdx.x; o < 2 * C; o += NT) {
-        double s = 0.0;
-        for (int r = 0; r < CS; ++r) s += cl.map_shared_rank(chan, r)[o];
-        tot[o] = (float)s;
+    for (int c = threadIdx.x; c < C; c += NT) {
+        double s1 = 0.0, sx = 0.0;
+        for (int r = 0; r < CS; ++r) { const double* rp = cl.map_shared_rank(chan, r); s1 += rp[c]; sx += rp[C + c]; }
+        const int g = c / cpg;
+        const double s2 = (double)gr[g] * (sx - (double)gm[g] * s1);       // sum dz*xhat
+        tot[c] = (float)s1; tot[C + c] = (float)s2;
         if (rank == 0) {
-            if (o < C) { if (a.dbeta) atomicAdd(a.dbeta + o, (float)s); }
-            else if (a.dgamma) atomicAdd(a.dgamma + (o - C), (float)s);
+            if (a.dbeta) atomicAdd(a.dbeta + c, (float)s1);
+            if (a.dgamma) atomicAdd(a.dgamma + c, (float)s2);
         }
     }
     cluster_arrive();                                        // remote reads done; waited for before exit
@@ -341,16 +362,18 @@ __global__ void __launch_bounds__(NT, 2) gn_bwd_kernel(GnP a) {
     }
     __syncthreads();
 
-    // ---- phase 2: dx (x and dy are L2 hits now)
+    // ---- phase 2: dx = rs*(dz*ga - A_g - xhat*B_g) = k0*dz - k1*x + k2   (x and dy/dz are L2 hits now)
     float csum[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) csum[i] = 0.f;
     if (m.active) {
-        float ra[VEC], rb[VEC];
+        float k0[VEC], k1[VEC], k2[VEC], rs[VEC], mr[VEC], ga[VEC], be[VEC];
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
-            const int g = min(c0 + i, C - 1) / cpg;
-            ra[i] = rs[i] * gA[g]; rb[i] = rs[i] * gB[g];
+            const int c = min(c0 + i, C - 1), g = c / cpg;
+            const float r_ = gr[g], m_ = gm[g] * gr[g], g_ = __ldg(a.gamma + c);
+            k0[i] = r_ * g_; k1[i] = r_ * r_ * gB[g]; k2[i] = m_ * r_ * gB[g] - r_ * gA[g];
+            rs[i] = r_; mr[i] = m_; ga[i] = g_; be[i] = __ldg(a.beta + c);      // only used when !STASH
         }
         for (int pb = p0 + m.prow; pb < p1; pb += U * m.ppi) {
             Raw<T, VEC> rx[U], rd[U], ro[U];
@@ -358,10 +381,9 @@ __global__ void __launch_bounds__(NT, 2) gn_bwd_kernel(GnP a) {
             for (int u = 0; u < U; ++u) {
                 const int p = pb + u * m.ppi;
                 if (p < p1) {
-                    int y, xx; split_pix(p, W, a.wshift, y, xx);
-                    ldraw<T, VEC>(a.x.at<T>(n, y, xx, c0), rx[u]);
-                    ldraw<T, VEC>(a.dy.at<T>(n, y, xx, c0), rd[u]);
-                    if (a.accumulate) ldraw<T, VEC>(a.o.at<T>(n, y, xx, c0), ro[u]);
+                    ldraw<T, VEC>(ax.at(xb, p), rx[u]);
+                    ldraw<T, VEC>(ad.at(db, p), rd[u]);
+                    if (a.accumulate) ldraw<T, VEC>(ao.at(ob, p), ro[u]);
                 }
             }
 #pragma unroll
@@ -371,23 +393,20 @@ __global__ void __launch_bounds__(NT, 2) gn_bwd_kernel(GnP a) {
                     float v[VEC], d[VEC], r[VEC];
                     unraw<T, VEC>(rx[u], v); unraw<T, VEC>(rd[u], d);
                     if (a.accumulate) unraw<T, VEC>(ro[u], r);
-                    uint32_t keep = 0xffffffffu;
-                    if (a.thr16 && !a.stash) keep = dropout_mask16<VEC>(dkey, ((uint64_t)n * HW + p) * C + c0, a.thr16);
+                    if (!STASH) {                                          // recompute dz (phase 1 could not leave it in dy)
+                        if (a.thr16) dropout_apply<VEC>(d, dkey, ebase + (uint32_t)p * (uint32_t)C, a.thr16, a.keep_scale);
+                        if (a.act) {
+#pragma unroll
+                            for (int i = 0; i < VEC; ++i) d[i] *= dsilu_f(fmaf(fmaf(v[i], rs[i], -mr[i]), ga[i], be[i]));
+                        }
+                    }
 #pragma unroll
                     for (int i = 0; i < VEC; ++i) {
-                        const float xh = fmaf(v[i], rs[i], -mr[i]);
-                        float dz = d[i];                                   // already dz when phase 1 stashed it
-                        if (!a.stash) {
-                            dz = ((keep >> i) & 1u) ? d[i] * a.keep_scale : 0.f;
-                            if (a.act) dz *= dsilu_f(fmaf(xh, ga[i], be[i]));
-                        }
-                        const float g = fmaf(dz * ga[i], rs[i], -ra[i]) - xh * rb[i];     // rs*(dz*ga - A - xh*B)
+                        const float g = fmaf(-v[i], k1[i], fmaf(d[i], k0[i], k2[i]));
                         r[i] = a.accumulate ? r[i] + g : g;
-                        if (sizeof(T) == 2) r[i] = __bfloat162float(__float2bfloat16_rn(r[i]));   // what is stored is what is summed
                         csum[i] += r[i];
                     }
-                    int y, xx; split_pix(p, W, a.wshift, y, xx);
-                    stv<T, VEC>(a.o.at<T>(n, y, xx, c0), r);
+                    stv<T, VEC>(ao.at(ob, p), r);
                 }
             }
         }
@@ -498,7 +517,8 @@ static int gn_bwd_impl(const ddpm_tensor* x, int dtype, int groups, const double
     const int HW = x->H * x->W, C = x->C;
     const size_t sm = sizeof(double) * 2 * C + sizeof(float) * (2 * C + 4 * groups);
 #define GO(T, VEC) { int cvs = C / VEC; if (cvs > NT) return DDPM_E_ARG; int cs = gn_cluster_size(HW, cvs); \
-        return launch_cluster(gn_bwd_kernel<T, VEC>, x->N * cs, cs, sm, st, p); }
+        if (p.stash) return launch_cluster(gn_bwd_kernel<T, VEC, true>, x->N * cs, cs, sm, st, p); \
+        return launch_cluster(gn_bwd_kernel<T, VEC, false>, x->N * cs, cs, sm, st, p); }
     if (dtype == DDPM_BF16) { if (vec_ok(x, 8, 2) && vec_ok(dy, 8, 2) && vec_ok(dx, 8, 2)) GO(bf16, 8) else GO(bf16, 1) }
     else if (dtype == DDPM_F32) { if (vec_ok(x, 4, 4) && vec_ok(dy, 4, 4) && vec_ok(dx, 4, 4)) GO(float, 4) else GO(float, 1) }
 #undef GO

@@ -20,6 +20,7 @@ ap.add_argument("--reps", type=int, default=10)
 ap.add_argument("--json", default=None)
 ap.add_argument("--epi", action="store_true", help="conv: also time with bias + time-bias + residual epilogue")
 ap.add_argument("--v1", action="store_true", help="conv: also time the first-generation kernel")
+ap.add_argument("--gnshape", default=None, help="restrict gn to one 'C,H'")
 ap.add_argument("--shape", default=None, help="restrict conv/wgrad to one 'Cin,Cout,H' (for ncu)")
 args = ap.parse_args()
 only = set(args.only.split(","))
@@ -74,6 +75,9 @@ if args.shape:
         CONV.append((v[0], v[1], v[2], 1) + ((v[3],) if len(v) > 3 else ()))
 GN = [(96, 64, 6), (96, 32, 1), (192, 32, 4), (192, 16, 5), (192, 8, 11), (384, 8, 1), (384, 16, 1), (384, 32, 1), (288, 64, 1)]
 
+if args.gnshape:
+    c_, h_ = [int(v) for v in args.gnshape.split(",")]
+    GN = [(c_, h_, 1)]
 E = engine.Exec(dev, _lib.BF16, True, True, rng=torch.tensor([1, 0], dtype=torch.int64, device=dev))
 
 if "conv" in only:
@@ -129,7 +133,7 @@ if "gn" in only:
         report("gn", f"apply+silu {c}@{hw}", timeit(lambda: engine.gn_apply(E, x, st, gn, 1, 0.0, 0, out=o), flush=fl), nbytes=4 * n, cnt=cnt)
         report("gn", f"FUSED fwd silu+drop {c}@{hw}", timeit(lambda: engine.gn_fwd(E, x, gn, 1, 0.1, 3, out=o), flush=fl), nbytes=4 * n, cnt=cnt)
         report("gn", f"apply+silu+drop {c}@{hw}", timeit(lambda: engine.gn_apply(E, x, st, gn, 1, 0.1, 3, out=o), flush=fl), nbytes=4 * n, cnt=cnt)
-        report("gn", f"bwd(silu+drop) {c}@{hw}", timeit(lambda: engine.gn_bwd(E, x, st, gn, 1, 0.1, 3, dy, dx, False), flush=fl), nbytes=6 * n, cnt=cnt)
+        report("gn", f"bwd(silu+drop) {c}@{hw}", timeit(lambda: engine.gn_bwd(E, x, st, gn, 1, 0.1, 3, dy, dx, False, dy_scratch=True), flush=fl), nbytes=6 * n, cnt=cnt)
         del x, o, dy, dx
 
 if "colsum" in only:
