@@ -242,6 +242,37 @@ def run_ours(args):
     value = world * B * args.steps / sec
     e2e = world * B * args.steps / sec_e2e
 
+    # ---- second half of the metric: DDIM-100 samples/s through the public sampler (bf16 autocast, eta = 0,
+    # batch-sharded over ranks with no communication; includes the grid PNG write of the reference API)
+    ddim = None
+    if not args.no_ddim:
+        import tempfile
+        from ddpm_diffusion_model_b200.testing.ddpim_inference import ddim_infer_sample
+        nb = args.ddim_batch
+        outp = os.path.join(tempfile.gettempdir(), f"ddim_bench_{rank}.png")
+
+        def ddim_call():
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                ddim_infer_sample(model, diff, n=nb * world, img_size=64, device=f"cuda:{local}", ema=None, out_path=outp,
+                                  seed=1234, steps=100, eta=0.0, shard=world > 1)
+        import contextlib, io
+        with contextlib.redirect_stdout(io.StringIO()):
+            ddim_call()                                   # warm-up (captures nothing persistent; pools / packs warm)
+            barrier()
+            t0 = time.perf_counter()
+            ddim_call()
+            barrier()
+            dt_ddim = time.perf_counter() - t0
+        if world > 1:
+            tt = torch.tensor([dt_ddim], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt_ddim = float(tt)
+        ddim = {"value": nb * world / dt_ddim, "unit": "samples/s", "steps": 100, "unet_evals": 99, "batch_per_gpu": nb,
+                "img": 64, "dtype": "bf16 autocast", "ms_per_eval": dt_ddim / 99 * 1e3,
+                "cuda_graph": os.environ.get("DDPM_B200_GRAPHS", "0") == "1",
+                "timed": "whole ddim_infer_sample call (wall clock, barrier + synchronize both sides), incl. grid PNG"}
+        model.train()
+
     roof = cpu = None
     if rank == 0:
         pk = peaks()
@@ -266,7 +297,7 @@ def run_ours(args):
             "e2e": {"value": e2e, "unit": "img/s", "h2d_bytes_per_step": B * 3 * 64 * 64 * 4, "d2h_bytes_per_step": 4,
                     "ms_per_step": sec_e2e / args.steps * 1e3},
             "gpu_launches": launches, "clocks": clk.summary(), "roofline": roof, "cpu_baseline": cpu,
-            "loss": last[0] if last else None, "pool_misses_in_timed_region": pool_misses,
+            "loss": last[0] if last else None, "pool_misses_in_timed_region": pool_misses, "ddim100": ddim,
             "train_tflops_per_gpu": TRAIN_GF_PER_IMG * 1e9 * B * args.steps / sec / 1e12,
         }
         print(json.dumps(line), flush=True)
@@ -282,6 +313,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=128)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-ddim", action="store_true", help="skip the DDIM-100 sampling leg")
+    ap.add_argument("--ddim-batch", type=int, default=256, help="images per GPU for the DDIM-100 leg")
     ap.add_argument("--profile", action="store_true", help="2 warm-up steps + 1 step, no JSON (for ncu)")
     args = ap.parse_args()
     if args.impl == "reference":

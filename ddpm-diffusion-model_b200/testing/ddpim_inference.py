@@ -4,7 +4,7 @@ import math
 
 import torch
 
-from ._common import initial_noise, sampling_weights, save_each, save_grid, to_image01
+from ._common import StepGraph, graphs_enabled, initial_noise, sampling_weights, save_each, save_grid, to_image01
 
 
 def build_ddim_schedule(diffusion, steps: int, schedule_kind: str = "t_linear", schedule_idx=None) -> list:
@@ -38,10 +38,17 @@ def ddim_infer_sample(model, diffusion, n: int = 36, img_size: int = 64, device:
         x = initial_noise(n, img_size, device, seed, shard)
         B = x.shape[0]
         sched = build_ddim_schedule(diffusion, steps, schedule_kind, schedule_idx)
-        for cur, prev in zip(sched[:-1], sched[1:]):
-            t = torch.full((B,), cur, device=x.device, dtype=torch.long)
-            tp = torch.full((B,), prev, device=x.device, dtype=torch.long)
-            x = diffusion.p_sample_step_ddim(model, x_t=x, t=t, t_prev=tp, eta=eta, clip_x0=True, noise=None)
+        if graphs_enabled() and len(sched) > 3:
+            sg = StepGraph(lambda x_, t_, tp_, z_: diffusion.p_sample_step_ddim(model, x_t=x_, t=t_, t_prev=tp_, eta=eta,
+                                                                                clip_x0=True, noise=z_), x, True)
+            for cur, prev in zip(sched[:-1], sched[1:]):
+                sg.run(cur, prev)                      # noise is drawn every step, like the reference (App. C.5)
+            x = sg.x
+        else:
+            for cur, prev in zip(sched[:-1], sched[1:]):
+                t = torch.full((B,), cur, device=x.device, dtype=torch.long)
+                tp = torch.full((B,), prev, device=x.device, dtype=torch.long)
+                x = diffusion.p_sample_step_ddim(model, x_t=x, t=t, t_prev=tp, eta=eta, clip_x0=True, noise=None)
         x = to_image01(x)
         r = int(math.sqrt(n))
         grid = save_grid(x, r if r * r == n else math.ceil(math.sqrt(n)), out_path)

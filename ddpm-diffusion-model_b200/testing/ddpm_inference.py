@@ -5,7 +5,7 @@ import math
 
 import torch
 
-from ._common import initial_noise, sampling_weights, save_each, save_grid, to_image01
+from ._common import StepGraph, graphs_enabled, initial_noise, sampling_weights, save_each, save_grid, to_image01
 
 
 @torch.no_grad()
@@ -16,9 +16,15 @@ def ddpm_infer_sample(model, diffusion, n: int = 36, img_size: int = 64, device:
     with sampling_weights(model, ema):
         x = initial_noise(n, img_size, device, seed, shard)
         B = x.shape[0]
-        for i in reversed(range(diffusion.T)):
-            t = torch.full((B,), i, device=x.device, dtype=torch.long)
-            x = diffusion.p_sample_step(model, x, t)
+        if graphs_enabled() and diffusion.T > 3:
+            sg = StepGraph(lambda x_, t_, tp_, z_: diffusion.p_sample_step(model, x_, t_, noise=z_), x, False)
+            for i in reversed(range(diffusion.T)):
+                sg.run(i, None)
+            x = sg.x
+        else:
+            for i in reversed(range(diffusion.T)):
+                t = torch.full((B,), i, device=x.device, dtype=torch.long)
+                x = diffusion.p_sample_step(model, x, t)
         x = to_image01(x)
         grid = save_grid(x, int(math.sqrt(n)), out_path)
         print(f"[INFER] Grid guardado en: {out_path}")

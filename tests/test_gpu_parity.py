@@ -623,6 +623,21 @@ def test_samplers_golden(golden, tmp_path):
         torch.randn, torch.randn_like = real_randn, real_like
 
 
+def test_sampler_cuda_graph_matches_eager(tmp_path, monkeypatch):
+    """Opt-in CUDA-graph replay of the sampler step gives bit-identical samples to the eager loop (same seed)."""
+    from ddpm_diffusion_model_b200.model.difussion_class import Diffusion
+    from ddpm_diffusion_model_b200.model.unet_backbone import UNetDenoiser
+    from ddpm_diffusion_model_b200.testing.ddpim_inference import ddim_infer_sample
+    torch.manual_seed(0)
+    model = UNetDenoiser(3, 32, (1, 2), 1, {8}, 64, 0.0, 2, 16, 16).to(dev()).eval()
+    d = Diffusion(T=200).to(dev())
+    outs = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("DDPM_B200_GRAPHS", flag)
+        outs.append(ddim_infer_sample(model, d, n=4, img_size=16, device="cuda", seed=7, steps=8, eta=0.5, out_path=str(tmp_path / f"g{flag}.png")))
+    assert torch.equal(outs[0], outs[1])
+
+
 def test_low_gpu_model_fp32_vs_oracle():
     """The BASELINE config-1 model (low-GPU UNet, 12.68 M params) at B=2: forward vs the CPU oracle."""
     from ddpm_diffusion_model_b200.model.unet_backbone import build_unet_64x64
