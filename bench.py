@@ -64,7 +64,7 @@ class ClockSampler:
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self.stop.wait(0.2)
+            self.stop.wait(0.05)
 
     def __enter__(self):
         self.th.start()
@@ -278,8 +278,13 @@ def run_ours(args):
         pk = peaks()
         fl, tt, detail = conv_roofline(dev, B)
         ach = fl / tt / 1e12
+        # traffic: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel at the 96->96@64 shape
+        # (B=128), from the committed `ncu --set full` capture profiles/r1_ncu_prof_conv_tc2_96_64.txt
+        # (107.4 MB read = the input tensor once, 54.4 MB written back before the kernel ended; the algorithmic
+        # bytes of that launch are 107 MB in + 107 MB out + 0.17 MB weights)
         roof = {"bound": "tensor", "achieved": ach, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": ach / pk["tf_burst"],
-                "traffic": None, "kernel": "implicit-GEMM conv fprop (3x3 s1 layers of the low-GPU UNet, B=%d)" % B,
+                "traffic": 161715200 if B == 128 else None, "traffic_shape": "96->96@64, B=128",
+                "kernel": "conv_tc2_kernel (tcgen05 cta_group::2 implicit GEMM; 3x3 s1 layers of the low-GPU UNet, count-weighted, B=%d)" % B,
                 "peak_source": pk["src"] + " bf16 burst (kernel timed alone)", "per_shape": detail,
                 "step_tensor_frac": (TRAIN_GF_PER_IMG * 1e9 * world * B * args.steps / sec) / (world * pk["tf_sus"] * 1e12)}
         if world == 1 and not args.no_cpu:
@@ -308,7 +313,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=128)
