@@ -180,6 +180,8 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
+    if args.tc_exp:
+        _lib.lib.ddpm_set_tc_mode(1 | (args.tc_exp << 4), 0)
     torch.manual_seed(0)
     model = build_unet_64x64(**LOW_GPU).to(dev)
     diff = Diffusion(T=1000, schedule="linear", beta_min=1e-4, beta_max=2e-2, img_size=64).to(dev)
@@ -318,6 +320,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=128)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--tc-exp", type=int, default=0, help="diagnostic flags for the conv kernel (timing experiments only; results are wrong)")
     ap.add_argument("--no-ddim", action="store_true", help="skip the DDIM-100 sampling leg")
     ap.add_argument("--ddim-batch", type=int, default=256, help="images per GPU for the DDIM-100 leg")
     ap.add_argument("--profile", action="store_true", help="2 warm-up steps + 1 step, no JSON (for ncu)")

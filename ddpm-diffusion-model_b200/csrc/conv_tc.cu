@@ -510,6 +510,19 @@ __device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {      // arrives
                  ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
 
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): one full 32-byte sector per lane and instruction.  The
+// epilogue's rows are 192-384 B apart, so every lane touches its own sector anyway; with 16-byte accesses each
+// sector was written (and, for residuals, read) in two halves by two instructions.
+struct U8 { uint4 lo, hi; };
+__device__ __forceinline__ void ldg256(const void* p, U8& v) {
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v.lo.x), "=r"(v.lo.y), "=r"(v.lo.z), "=r"(v.lo.w), "=r"(v.hi.x), "=r"(v.hi.y), "=r"(v.hi.z), "=r"(v.hi.w) : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint4& lo, const uint4& hi) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"l"(p), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
+}
+
 struct Tc2Params {
     TV out, res;
     const float* bias; const float* tbias; int tbias_pitch; int bias_n;
@@ -523,6 +536,9 @@ struct Tc2Params {
     int pix_tiles, items;
     int has_res, accum, sub, exp;
     int vec_bias, vec_tbias;      // 16-byte aligned -> float4 loads in the epilogue
+    int v256;                     // out (and res) rows are 32-byte aligned -> 256-bit loads / stores
+    int b_res;                    // 1: this CTA's half of the weight tile (all K-chunks, all taps) stays resident in shared
+                                  //    memory -- loaded once, with the first item's stages -- and only A patches stream
 };
 
 template <int MT, int TAPS>
@@ -531,7 +547,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_c
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* ring = smem;
-    uint64_t* bars = (uint64_t*)(ring + (size_t)p.S * p.stage_bytes);
+    uint8_t* bres = ring + (size_t)p.S * p.stage_bytes;                                   // resident weights (b_res only)
+    uint64_t* bars = (uint64_t*)(bres + (p.b_res ? (size_t)(p.Cin / KC) * p.b_chunk_bytes : 0));
     uint64_t* full = bars;            uint64_t* empty = full + p.S;
     uint64_t* tfull = empty + p.S;    uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
@@ -572,16 +589,17 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_c
                     const int kc0 = st * p.KS, nk = min(p.KS, KCH - kc0);
                     const uint32_t fbar = mapa_u32(smem_u32(&full[s]), 0);
                     const bool skipA = (p.exp & 1) && g >= (uint32_t)p.S, skipB = (p.exp & 2) && g >= (uint32_t)p.S;   // diagnostics
-                    const uint32_t tx = (uint32_t)(2 * nk * ((skipA ? 0 : p.P * 32) + (skipB ? 0 : p.b_chunk_bytes)));
+                    const bool loadB = !skipB && !(p.b_res && it != pair);       // resident weights arrive with the first item only
+                    const uint32_t tx = (uint32_t)(2 * nk * ((skipA ? 0 : p.P * 32) + (loadB ? p.b_chunk_bytes : 0)));
                     if (leader) { if (tx) mbar_expect_tx(&full[s], tx); else mbar_arrive(&full[s]); }
                     uint8_t* sbase = ring + (size_t)s * p.stage_bytes;
                     for (int k = 0; k < nk; ++k) {
-                        uint8_t* adst = sbase + (size_t)k * (p.a_chunk_bytes + p.b_chunk_bytes);
-                        uint8_t* bdst = adst + p.a_chunk_bytes;
+                        uint8_t* adst = sbase + (size_t)k * (p.a_chunk_bytes + (p.b_res ? 0 : p.b_chunk_bytes));
+                        uint8_t* bdst = p.b_res ? bres + (size_t)(kc0 + k) * p.b_chunk_bytes : adst + p.a_chunk_bytes;
                         const int row0 = Q0 - halo_rows;
                         for (int r = 0; r < p.P && !skipA; r += p.seg)
                             tma2_load_2d(adst + (size_t)r * 32, &tmA, fbar, (kc0 + k) * KC, row0 + r);
-                        if (!skipB) tma2_load_3d(bdst, &tmB, fbar, (kc0 + k) * KC, nrow0, 0);
+                        if (loadB) tma2_load_3d(bdst, &tmB, fbar, (kc0 + k) * KC, nrow0, 0);
                     }
                 }
             }
@@ -598,8 +616,9 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_c
 #pragma unroll
             for (int tap = 0; tap < TAPS; ++tap) tapoff[tap] = TAPS == 9 ? (uint32_t)(((tap / 3) * p.Wp + (tap % 3)) * 2) : 0u;
             const uint32_t b_tap = (uint32_t)p.NT;                       // (NT/2 rows * 32 B) >> 4
-            const uint32_t chunk16 = (uint32_t)((p.a_chunk_bytes + p.b_chunk_bytes) >> 4), a16 = (uint32_t)(p.a_chunk_bytes >> 4);
+            const uint32_t chunk16 = (uint32_t)((p.a_chunk_bytes + (p.b_res ? 0 : p.b_chunk_bytes)) >> 4), a16 = (uint32_t)(p.a_chunk_bytes >> 4);
             const uint32_t ring_lo = desc_lo(smem_u32(ring), 16u), stage16 = (uint32_t)(p.stage_bytes >> 4);
+            const uint32_t bres_lo = desc_lo(smem_u32(bres), 16u), bchunk16 = (uint32_t)(p.b_chunk_bytes >> 4);
             uint32_t g = 0, j = 0;
             for (int it = pair; it < p.items; it += npairs, ++j) {
                 const uint32_t buf = j & 1, bph = (j >> 1) & 1;
@@ -614,7 +633,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_c
                     const int nk = min(p.KS, KCH - st * p.KS);
                     uint32_t a_lo = ring_lo + s * stage16;
                     for (int k = 0; k < nk; ++k, a_lo += chunk16) {
-                        const uint32_t b_lo = a_lo + a16;
+                        const uint32_t b_lo = p.b_res ? bres_lo + (uint32_t)(st * p.KS + k) * bchunk16 : a_lo + a16;
 #pragma unroll
                         for (int tap = 0; tap < TAPS; ++tap) {
                             const uint64_t bdesc = desc_pack(b_lo + (uint32_t)tap * b_tap, hi);
@@ -648,11 +667,12 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_c
             const int pt = it / p.n_tiles, ntile = it - pt * p.n_tiles;
             const int Q0 = pt * (2 * tile_rows) + (int)rank * tile_rows;
             const int n0 = ntile * p.NT;
-            mbar_wait(&tfull[buf], bph);
-            tc_fence_after();
-            const uint32_t dbase = tmem_base + buf * (uint32_t)cols_per_buf;
-#pragma unroll 1
-            for (int mt = 0; mt < ((p.exp & 4) ? 0 : MT); ++mt) {      // exp bit 2: skip the epilogue (diagnostic)
+            // Row addressing for this item is done BEFORE waiting for the accumulators, and the residual / accumulate
+            // rows are prefetched into L2 while the MMAs are still running: the epilogue was latency-bound on
+            // those reads (96->96@64: 75 us plain vs 140 us with a residual).
+            bf16* orow_a[MT]; const bf16* rrow_a[MT]; const float* tb_a[MT];
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
                 const int Q = Q0 + mt * 128 + qd * 32 + lane;
                 bool valid = Q < p.Qtot;
                 int n = 0, y = 0, x = 0;
@@ -662,9 +682,22 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_c
                     valid = y >= 0 && y < p.H && x >= 0 && x < p.W;
                     if (p.sub) { valid = valid && ((y | x) & 1) == 0; y >>= 1; x >>= 1; }
                 }
-                bf16* orow = valid ? p.out.at<bf16>(n, y, x, n0) : nullptr;
-                const bf16* rrow = (valid && p.has_res) ? p.res.at<bf16>(n, y, x, n0) : nullptr;
-                const float* tb = (valid && p.tbias) ? p.tbias + (size_t)n * p.tbias_pitch + n0 : nullptr;
+                orow_a[mt] = valid ? p.out.at<bf16>(n, y, x, n0) : nullptr;
+                rrow_a[mt] = (valid && p.has_res && !(p.exp & 16)) ? p.res.at<bf16>(n, y, x, n0) : nullptr;   // exp bit 4: timing-only
+                tb_a[mt] = (valid && p.tbias && !(p.exp & 16)) ? p.tbias + (size_t)n * p.tbias_pitch + n0 : nullptr;
+                const bf16* pf = rrow_a[mt] ? rrow_a[mt] : ((p.accum && valid) ? orow_a[mt] : nullptr);
+                if (pf) {
+                    for (int c = blk_lo << 4; c < (blk_hi << 4); c += 64)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + c));
+                }
+            }
+            mbar_wait(&tfull[buf], bph);
+            tc_fence_after();
+            const uint32_t dbase = tmem_base + buf * (uint32_t)cols_per_buf;
+#pragma unroll
+            for (int mt = 0; mt < ((p.exp & 4) ? 0 : MT); ++mt) {      // exp bit 2: skip the epilogue (diagnostic)
+                bf16* orow = orow_a[mt]; const bf16* rrow = rrow_a[mt]; const float* tb = tb_a[mt];
+                const bool valid = orow != nullptr;
                 // (staging the tile in shared memory to emit full 128-byte lines per store instruction was measured
                 // SLOWER -- 153 vs 117 us at 96->96@64: the kernel is bound by L2 traffic, not store coalescing)
                 // 64 output channels per trip: all TMEM / residual / accumulate loads of the trip are in flight
@@ -679,8 +712,14 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_c
                         const int c = (blk + q) << 4;
                         if (blk + q < blk_hi) {
                             tmem_ld16(dbase + ((uint32_t)(qd * 32) << 16) + (uint32_t)(mt * p.NT + c), r[q]);
-                            if (rrow) { rr[q][0] = *reinterpret_cast<const uint4*>(rrow + c); rr[q][1] = *reinterpret_cast<const uint4*>(rrow + c + 8); }
-                            if (p.accum && valid) { ra[q][0] = *reinterpret_cast<const uint4*>(orow + c); ra[q][1] = *reinterpret_cast<const uint4*>(orow + c + 8); }
+                            if (rrow) {
+                                if (p.v256) { U8 t; ldg256(rrow + c, t); rr[q][0] = t.lo; rr[q][1] = t.hi; }
+                                else { rr[q][0] = *reinterpret_cast<const uint4*>(rrow + c); rr[q][1] = *reinterpret_cast<const uint4*>(rrow + c + 8); }
+                            }
+                            if (p.accum && valid && !(p.exp & 16)) {
+                                if (p.v256) { U8 t; ldg256(orow + c, t); ra[q][0] = t.lo; ra[q][1] = t.hi; }
+                                else { ra[q][0] = *reinterpret_cast<const uint4*>(orow + c); ra[q][1] = *reinterpret_cast<const uint4*>(orow + c + 8); }
+                            }
                         }
                     }
                     tmem_ld_wait();
@@ -724,7 +763,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_c
                                     v[2 * i] += fa.x; v[2 * i + 1] += fa.y; v[8 + 2 * i] += fb.x; v[8 + 2 * i + 1] += fb.y;
                                 }
                             }
-                            if (p.accum) {
+                            if (p.accum && !(p.exp & 16)) {
                                 const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&ra[q][0]);
                                 const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&ra[q][1]);
 #pragma unroll
@@ -742,8 +781,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_c
                                 h1[i] = __floats2bfloat162_rn(v[8 + 2 * i], v[8 + 2 * i + 1]);
                             }
                             if (!(p.exp & 8) || o0.x == 0x12345678u) {        // exp bit 3: no global stores (diagnostic)
-                                *reinterpret_cast<uint4*>(orow + c) = o0;
-                                *reinterpret_cast<uint4*>(orow + c + 8) = o1;
+                                if (p.v256) stg256(orow + c, o0, o1);
+                                else { *reinterpret_cast<uint4*>(orow + c) = o0; *reinterpret_cast<uint4*>(orow + c + 8) = o1; }
                             }
                         }
                     }
@@ -770,7 +809,12 @@ static int conv_tc2_launch(const ddpm_conv_args* a, cudaStream_t st) {
     p.has_res = a->res.ptr != nullptr; p.res = p.has_res ? TV(a->res) : TV(a->out);
     p.bias = a->bias; p.tbias = a->tbias; p.tbias_pitch = a->tbias_pitch;
     p.bias_n = a->bias_n > 0 ? a->bias_n : a->out.C;
-    p.Cin = a->in.C; p.Cout = a->out.C; p.NT = pick_nt(p.Cout); p.n_tiles = p.Cout / p.NT;
+    p.Cin = a->in.C; p.Cout = a->out.C; p.NT = pick_nt(p.Cout);
+    // Channel tiles of at most 128: with MT = 2 the weight slab is then shared by 256 pixel rows per CTA and the
+    // A-patch halo is amortised over two M-tiles -> 26 % less L2->SM traffic per FLOP than NT = 192, MT = 1
+    // (measured +8..14 % on every Cout = 192 layer); bit 5 of the experiment flags restores the wide tile.
+    if (!(g_tc_exp & 32) && p.NT % 32 == 0 && p.NT > 128) p.NT /= 2;
+    p.n_tiles = p.Cout / p.NT;
     p.taps = a->KH * a->KW;
     p.Hp = a->in.H + 2; p.Wp = a->in.W + 2; p.H = a->in.H; p.W = a->in.W;
     p.Qtot = a->in.N * p.Hp * p.Wp;
@@ -778,6 +822,8 @@ static int conv_tc2_launch(const ddpm_conv_args* a, cudaStream_t st) {
     p.sub = a->stride == 2 ? 1 : 0; p.exp = g_tc_exp;
     p.vec_bias = a->bias && (((uintptr_t)a->bias & 15) == 0);
     p.vec_tbias = a->tbias && (((uintptr_t)a->tbias & 15) == 0) && (a->tbias_pitch % 4 == 0);
+    p.v256 = (((uintptr_t)a->out.ptr & 31) == 0) && (a->out.pitch % 16 == 0) &&
+             (!a->res.ptr || ((((uintptr_t)a->res.ptr & 31) == 0) && (a->res.pitch % 16 == 0))) && !(g_tc_exp & 128);
     int MT = 256 / p.NT; if (MT > 2) MT = 2; if (MT < 1) MT = 1;
     // small problems: prefer more, smaller items so that every SM pair gets one
     if (MT == 2 && (int64_t)ceil_div(p.Qtot, 512) * p.n_tiles < sm_count() / 2) MT = 1;
@@ -792,13 +838,27 @@ static int conv_tc2_launch(const ddpm_conv_args* a, cudaStream_t st) {
     p.b_chunk_bytes = p.taps * (p.NT / 2) * 32;             // multiple of 256: NT/2 is a multiple of 8
     const int KCH = p.Cin / KC;
     p.KS = p.taps == 9 ? 1 : (KCH < 4 ? KCH : 4);
-    p.stage_bytes = (p.KS * (p.a_chunk_bytes + p.b_chunk_bytes) + 1023) & ~1023;
     const int budget = 212 * 1024;
-    p.S = budget / p.stage_bytes; if (p.S > 12) p.S = 12;
-    if (p.S < 2) return DDPM_E_ARG;
     p.pix_tiles = ceil_div(p.Qtot, 256 * MT);
     p.items = p.pix_tiles * p.n_tiles;
-    size_t smem = (size_t)p.S * p.stage_bytes + 8 * (2 * p.S + 4) + 16 + 1024;
+    int pairs = sm_count() / 2; if (pairs > p.items) pairs = p.items; if (pairs < 1) pairs = 1;
+    // Weights resident in shared memory when this CTA's half tile (all K-chunks, all taps) leaves room for a >= 3-deep
+    // A ring and every CTA pair sees several items: then only activations stream (14.8 instead of 30.8 B/clk/SM at NT=96).
+    p.b_res = 0;
+    if (p.taps == 9 && !(g_tc_exp & 64)) {
+        const int bres_bytes = KCH * p.b_chunk_bytes;
+        const int pr = pairs - pairs % p.n_tiles;             // a pair keeps ONE channel tile: pairs must be a multiple of n_tiles
+        if (bres_bytes + 3 * p.a_chunk_bytes <= budget && pr >= p.n_tiles && p.items >= 3 * pr) { p.b_res = 1; pairs = pr; }
+    }
+    if (p.b_res) {
+        p.stage_bytes = p.a_chunk_bytes;
+        p.S = (budget - KCH * p.b_chunk_bytes) / p.stage_bytes; if (p.S > 12) p.S = 12;
+    } else {
+        p.stage_bytes = (p.KS * (p.a_chunk_bytes + p.b_chunk_bytes) + 1023) & ~1023;
+        p.S = budget / p.stage_bytes; if (p.S > 12) p.S = 12;
+    }
+    if (p.S < 2) return DDPM_E_ARG;
+    size_t smem = (size_t)p.S * p.stage_bytes + (p.b_res ? (size_t)KCH * p.b_chunk_bytes : 0) + 8 * (2 * p.S + 4) + 16 + 1024;
 
     CUtensorMap tmA, tmB;
     {
@@ -811,7 +871,6 @@ static int conv_tc2_launch(const ddpm_conv_args* a, cudaStream_t st) {
         uint32_t bb[3] = {KC, (uint32_t)(p.NT / 2), (uint32_t)p.taps};
         if (encode(&tmB, (void*)a->w, 3, db, sb, bb, CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
     }
-    int pairs = sm_count() / 2; if (pairs > p.items) pairs = p.items; if (pairs < 1) pairs = 1;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(TC2_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute at[1];

@@ -88,7 +88,7 @@ if "conv" in only:
         x = E.act(B, hw, hw, ci); x.interior().normal_()
         y = E.act(B, hw, hw, co)
         fl = 2.0 * B * hw * hw * co * ci * ks * ks
-        modes = [(1, "")] + ([(1 | (3 << 4), " skipAB"), (1 | (4 << 4), " skipEpi"), (1 | (8 << 4), " skipStores"), (1 | (7 << 4), " skipAB+Epi")] if args.exp else [])
+        modes = [(1, "")] + ([(1 | (3 << 4), " skipAB"), (1 | (4 << 4), " skipEpi"), (1 | (8 << 4), " skipStores"), (1 | (7 << 4), " skipAB+Epi"), (1 | (32 << 4), " skip(NT/2)")] if args.exp else [])
         for mode, tag in modes:
             _lib.lib.ddpm_set_tc_mode(mode, 0)
             sec = timeit(lambda: engine.conv(E, x, wf, y, ks, 1, ks // 2))
