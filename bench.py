@@ -131,14 +131,19 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def conv_roofline(device, batch, reps=5):
+C256_SHAPES = [(128, 128, 256, 10), (128, 128, 128, 9), (256, 256, 64, 9), (256, 128, 256, 1), (256, 256, 128, 1),
+               (512, 512, 16, 12), (384, 128, 128, 1), (256, 256, 32, 9), (512, 256, 64, 1)]
+
+
+def conv_roofline(device, batch, reps=5, shapes=None):
     """Time the implicit-GEMM convolution kernel alone (fprop shapes of the low-GPU UNet at the bench
     batch), CUDA events on the launching stream.  Returns (flops per pass, seconds per pass, detail)."""
     from ddpm_diffusion_model_b200 import _lib, engine
     E = engine.Exec(device, _lib.BF16, False, False)
     # (Cin, Cout, H, count) -- SURVEY.md Appendix A.1, 3x3 s1 rows that make up 90 % of the FLOPs
-    shapes = [(96, 96, 64, 5), (192, 192, 32, 5), (192, 192, 64, 1), (288, 96, 64, 1), (384, 192, 32, 1),
-              (192, 192, 16, 6), (192, 192, 8, 9), (96, 192, 32, 1), (384, 192, 16, 1)]
+    if shapes is None:
+        shapes = [(96, 96, 64, 5), (192, 192, 32, 5), (192, 192, 64, 1), (288, 96, 64, 1), (384, 192, 32, 1),
+                  (192, 192, 16, 6), (192, 192, 8, 9), (96, 192, 32, 1), (384, 192, 16, 1)]
     tot_f, tot_t, detail = 0.0, 0.0, []
     for ci, co, hw, cnt in shapes:
         w = torch.nn.Parameter(torch.randn(co, ci, 3, 3, device=device) * 0.02)
@@ -183,13 +188,26 @@ def run_ours(args):
     if args.tc_exp:
         _lib.lib.ddpm_set_tc_mode(1 | (args.tc_exp << 4), 0)
     torch.manual_seed(0)
-    model = build_unet_64x64(**LOW_GPU).to(dev)
-    diff = Diffusion(T=1000, schedule="linear", beta_min=1e-4, beta_max=2e-2, img_size=64).to(dev)
-    opt = torch.optim.AdamW(model.parameters(), lr=2e-4, betas=(0.9, 0.999), weight_decay=0.0)
-    ema = EMA(model, decay=0.9995)
+    c256 = args.config == "celeba256"
+    IMG = 256 if c256 else 64
+    if c256:
+        # BASELINE.json configs[2]: CelebA256 attention UNet (63.1 M params), bf16, batch 32 per GPU
+        from ddpm_diffusion_model_b200.model.unet_backbone import UNetDenoiser
+        if args.batch == 128:
+            B = 32
+        model = UNetDenoiser(3, 128, (1, 1, 2, 2, 4), 2, {16}, 512, 0.1, 4, 64, 256).to(dev)
+        opt = torch.optim.AdamW(model.parameters(), lr=2e-4, betas=(0.9, 0.999), weight_decay=0.005)
+        ema_decay, gf_train = 0.9997, 1257.3
+        args.no_ddim = True
+    else:
+        model = build_unet_64x64(**LOW_GPU).to(dev)
+        opt = torch.optim.AdamW(model.parameters(), lr=2e-4, betas=(0.9, 0.999), weight_decay=0.0)
+        ema_decay, gf_train = 0.9995, TRAIN_GF_PER_IMG
+    diff = Diffusion(T=1000, schedule="linear", beta_min=1e-4, beta_max=2e-2, img_size=IMG).to(dev)
+    ema = EMA(model, decay=ema_decay)
     scaler = make_grad_scaler("cuda", True)
     torch.manual_seed(7 + rank)
-    x_host = torch.empty(B, 3, 64, 64).uniform_(-1, 1).pin_memory()
+    x_host = torch.empty(B, 3, IMG, IMG).uniform_(-1, 1).pin_memory()
     y_host = torch.zeros(B)
     x_dev = x_host.to(dev)
 
@@ -278,17 +296,17 @@ def run_ours(args):
     roof = cpu = None
     if rank == 0:
         pk = peaks()
-        fl, tt, detail = conv_roofline(dev, B)
+        fl, tt, detail = conv_roofline(dev, B, shapes=C256_SHAPES if c256 else None)
         ach = fl / tt / 1e12
         # traffic: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel at the 96->96@64 shape
         # (B=128), from the committed `ncu --set full` capture profiles/r1_ncu_prof_conv_tc2_96_64.txt
         # (107.4 MB read = the input tensor once, 54.4 MB written back before the kernel ended; the algorithmic
         # bytes of that launch are 107 MB in + 107 MB out + 0.17 MB weights)
         roof = {"bound": "tensor", "achieved": ach, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": ach / pk["tf_burst"],
-                "traffic": 161715200 if B == 128 else None, "traffic_shape": "96->96@64, B=128",
-                "kernel": "conv_tc2_kernel (tcgen05 cta_group::2 implicit GEMM; 3x3 s1 layers of the low-GPU UNet, count-weighted, B=%d)" % B,
+                "traffic": 161715200 if (B == 128 and not c256) else None, "traffic_shape": "96->96@64, B=128",
+                "kernel": "conv_tc2_kernel (tcgen05 cta_group::2 implicit GEMM; 3x3 s1 layers of the %s UNet, count-weighted, B=%d)" % ("CelebA256" if c256 else "low-GPU", B),
                 "peak_source": pk["src"] + " bf16 burst (kernel timed alone)", "per_shape": detail,
-                "step_tensor_frac": (TRAIN_GF_PER_IMG * 1e9 * world * B * args.steps / sec) / (world * pk["tf_sus"] * 1e12)}
+                "step_tensor_frac": (gf_train * 1e9 * world * B * args.steps / sec) / (world * pk["tf_sus"] * 1e12)}
         if world == 1 and not args.no_cpu:
             ips, dt, cores = cpu_train_imgs_per_s(2, 1)
             cpu = {"value": ips, "unit": "img/s", "cores": cores, "kind": "port",
@@ -298,14 +316,15 @@ def run_ours(args):
             "metric": "train_img_per_s", "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "CelebA64 low-GPU UNet (12.68M) training step: bf16 autocast + GradScaler + AdamW + EMA + clip",
-                       "batch_per_gpu": B, "global_batch": B * world, "img": 64, "T": 1000, "parallelism": f"dp{world}",
+            "config": {"workload": ("CelebA256 attention UNet (63.1M)" if c256 else "CelebA64 low-GPU UNet (12.68M)") +
+                       " training step: bf16 autocast + GradScaler + AdamW + EMA + clip",
+                       "batch_per_gpu": B, "global_batch": B * world, "img": IMG, "T": 1000, "parallelism": f"dp{world}",
                        "l2": "working set per step (~3 GB of activations) exceeds the 126 MB L2; no explicit flush"},
-            "e2e": {"value": e2e, "unit": "img/s", "h2d_bytes_per_step": B * 3 * 64 * 64 * 4, "d2h_bytes_per_step": 4,
+            "e2e": {"value": e2e, "unit": "img/s", "h2d_bytes_per_step": B * 3 * IMG * IMG * 4, "d2h_bytes_per_step": 4,
                     "ms_per_step": sec_e2e / args.steps * 1e3},
             "gpu_launches": launches, "clocks": clk.summary(), "roofline": roof, "cpu_baseline": cpu,
             "loss": last[0] if last else None, "pool_misses_in_timed_region": pool_misses, "ddim100": ddim,
-            "train_tflops_per_gpu": TRAIN_GF_PER_IMG * 1e9 * B * args.steps / sec / 1e12,
+            "train_tflops_per_gpu": gf_train * 1e9 * B * args.steps / sec / 1e12,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -320,6 +339,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=128)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--config", default="low64", choices=["low64", "celeba256"],
+                    help="low64: BASELINE configs[1] (default, the metric's workload); celeba256: configs[2] (batch 32/GPU)")
     ap.add_argument("--tc-exp", type=int, default=0, help="diagnostic flags for the conv kernel (timing experiments only; results are wrong)")
     ap.add_argument("--no-ddim", action="store_true", help="skip the DDIM-100 sampling leg")
     ap.add_argument("--ddim-batch", type=int, default=256, help="images per GPU for the DDIM-100 leg")

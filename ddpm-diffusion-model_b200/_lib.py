@@ -36,7 +36,8 @@ class WgradArgs(C.Structure):
     _fields_ = [("act", Tensor), ("dy", Tensor), ("dw", C.c_void_p), ("KH", C.c_int32),
                 ("KW", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32), ("a_silu", C.c_int32),
                 ("dtype", C.c_int32), ("prefer_tc", C.c_int32), ("workspace", C.c_void_p),
-                ("workspace_bytes", C.c_int64), ("cin_valid", C.c_int32), ("cout_valid", C.c_int32)]
+                ("workspace_bytes", C.c_int64), ("cin_valid", C.c_int32), ("cout_valid", C.c_int32),
+                ("dbias", C.c_void_p)]
 
 
 class AdamHyper(C.Structure):
@@ -98,6 +99,8 @@ def _load() -> C.CDLL:
     path = _build.LIB
     if not os.path.exists(path) or (os.environ.get("DDPM_B200_REBUILD") == "1"):
         path = _build.build()          # raises if nvcc is missing or the build fails
+    if os.environ.get("DDPM_B200_LIB"):                 # A/B measurements against another build of the same ABI
+        path = os.environ["DDPM_B200_LIB"]
     lib = C.CDLL(path)
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)        # AttributeError if the ABI symbol is missing

@@ -39,5 +39,11 @@ extern "C" int ddpm_conv_wgrad(const ddpm_wgrad_args* a, void* stream) {
     if (a->dy.W != (a->act.W + 2 * a->pad - a->KW) / a->stride + 1) return DDPM_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     if (a->prefer_tc && !g_force_simt && a->workspace && wgrad_tc_supported(a)) return wgrad_tc_launch(a, st);
+    if (a->dbias) {                      // CUDA-core path: the bias gradient is a separate column sum of dy
+        ddpm_tensor d = a->dy;
+        if (a->cout_valid > 0) d.C = a->cout_valid;
+        int rc = ddpm_colsum(&d, a->dtype, nullptr, a->dbias, stream);
+        if (rc) return rc;
+    }
     return wgrad_simt_launch(a, st);
 }

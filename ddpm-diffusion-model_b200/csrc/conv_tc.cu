@@ -20,6 +20,7 @@
 // for fprop and, with flipped/transposed weights, dgrad.
 #include "common.cuh"
 #include <cuda.h>
+#include <type_traits>
 #include <cudaTypedefs.h>
 
 #define TC_THREADS 192
@@ -912,18 +913,27 @@ struct WgTcParams {
     int stage_bytes, tmem_cols;
     int ntap;                   // taps per CTA: 3 (one filter row of a 3x3) or 1 (1x1)
     int CinV, CoutV;            // unpadded channel counts of the fp32 gradient
+    // bias gradient for free: CTAs of group 0 run one extra N=16 MMA per K-step against a tile of ones,
+    // D_bias[co][*] = sum_Q dY[Q][co] (halo rows of dY are zero), instead of a separate pass over dY
+    float* ws_bias;             // [split][mtile][128] partials (NULL: no bias gradient)
+    float* dbias;               // fp32 [CoutV], accumulated by the reduce kernel
 };
 
 __global__ void __launch_bounds__(TC_THREADS) wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY,
                                                                const __grid_constant__ CUtensorMap tmA, WgTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t* full = (uint64_t*)(smem + (size_t)WG_STAGES * p.stage_bytes);
+    uint8_t* ones = smem + (size_t)WG_STAGES * p.stage_bytes;            // [16 px][64 ch] of bf16 1.0 (2 KB, 1024-aligned)
+    uint64_t* full = (uint64_t*)(ones + 2048);
     uint64_t* empty = full + WG_STAGES;
     uint64_t* acc_full = empty + WG_STAGES;
     uint32_t* tmem_slot = (uint32_t*)(acc_full + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int split = blockIdx.x, grp = blockIdx.y, mtile = blockIdx.z;
+    // the K-steps of the bias reduction are dealt round-robin to the gridDim.y groups that stream the same dY
+    // rows (putting all of them on group 0 made those CTAs the critical path: +11..16 % kernel time)
+    const bool do_bias = p.ws_bias != nullptr;
+    const int ngrp = gridDim.y;
     const int ky = grp / p.n_tiles, ntile = grp - ky * p.n_tiles;
     const int m0 = mtile * 128, n0 = ntile * p.NT;
     const int s_beg = split * p.stages_per_cta;
@@ -937,10 +947,15 @@ __global__ void __launch_bounds__(TC_THREADS) wgrad_tc_kernel(const __grid_const
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    if (do_bias && warp >= 2) {
+        for (int i = threadIdx.x - 64; i < 2048 / 4; i += TC_THREADS - 64) reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;
+        fence_proxy_async();                             // generic-proxy writes -> visible to the tensor core's async proxy
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t bias_col = (uint32_t)(p.ntap * p.NT);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -968,25 +983,37 @@ __global__ void __launch_bounds__(TC_THREADS) wgrad_tc_kernel(const __grid_const
             const uint32_t a_lo0 = desc_lo(smem_u32(smem) + (uint32_t)y_bytes, (uint32_t)(WG_ROWS * 128));
             const uint32_t stage16 = (uint32_t)(p.stage_bytes >> 4);
             const bool three = p.ntap == 3;
-            uint32_t acc = 0;
-            for (int i = 0; i < nst; ++i) {
-                const uint32_t s = (uint32_t)(i % WG_STAGES); const uint32_t ph = (i / WG_STAGES) & 1;
-                mbar_wait(&full[s], ph);
-                tc_fence_after();
-                const uint32_t y_lo = y_lo0 + s * stage16, a_lo = a_lo0 + s * stage16;
+            const uint32_t idesc_b = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
+            const uint64_t ones_desc = desc_pack(desc_lo(smem_u32(ones), 2048u), hi);
+            // two copies of the loop: a predicated-off bias MMA in the common loop cost 11 % (measured A/B)
+            auto run = [&](auto with_bias) {
+                constexpr bool BIAS = decltype(with_bias)::value;
+                uint32_t acc = 0, accb = 0;
+                int kmod = ((s_beg * (WG_KQ / 16)) % ngrp);                 // (global K-step index) mod ngrp
+                for (int i = 0; i < nst; ++i) {
+                    const uint32_t s = (uint32_t)(i % WG_STAGES); const uint32_t ph = (i / WG_STAGES) & 1;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t y_lo = y_lo0 + s * stage16, a_lo = a_lo0 + s * stage16;
 #pragma unroll
-                for (int ks = 0; ks < WG_KQ / 16; ++ks) {
-                    const uint64_t ydesc = desc_pack(y_lo + (uint32_t)(ks * 16 * 128 / 16), hi);
-                    if (el) umma_bf16(tmem_base, ydesc, desc_pack(a_lo + (uint32_t)((ks * 16) * 8), hi), idesc, ks == 0 ? acc : 1u);
-                    if (three && el) {
-                        umma_bf16(tmem_base + (uint32_t)p.NT, ydesc, desc_pack(a_lo + (uint32_t)((ks * 16 + 1) * 8), hi), idesc, ks == 0 ? acc : 1u);
-                        umma_bf16(tmem_base + (uint32_t)(2 * p.NT), ydesc, desc_pack(a_lo + (uint32_t)((ks * 16 + 2) * 8), hi), idesc, ks == 0 ? acc : 1u);
+                    for (int ks = 0; ks < WG_KQ / 16; ++ks) {
+                        const uint64_t ydesc = desc_pack(y_lo + (uint32_t)(ks * 16 * 128 / 16), hi);
+                        if (el) umma_bf16(tmem_base, ydesc, desc_pack(a_lo + (uint32_t)((ks * 16) * 8), hi), idesc, ks == 0 ? acc : 1u);
+                        if (three && el) {
+                            umma_bf16(tmem_base + (uint32_t)p.NT, ydesc, desc_pack(a_lo + (uint32_t)((ks * 16 + 1) * 8), hi), idesc, ks == 0 ? acc : 1u);
+                            umma_bf16(tmem_base + (uint32_t)(2 * p.NT), ydesc, desc_pack(a_lo + (uint32_t)((ks * 16 + 2) * 8), hi), idesc, ks == 0 ? acc : 1u);
+                        }
+                        if (BIAS) {
+                            if (kmod == grp) { if (el) umma_bf16(tmem_base + bias_col, ydesc, ones_desc, idesc_b, accb); accb = 1; }
+                            if (++kmod == ngrp) kmod = 0;
+                        }
                     }
+                    acc = 1;
+                    if (el) umma_commit(&empty[s]);
+                    __syncwarp();
                 }
-                acc = 1;
-                if (el) umma_commit(&empty[s]);
-                __syncwarp();
-            }
+            };
+            if (do_bias) run(std::true_type{}); else run(std::false_type{});
             if (el) umma_commit(acc_full);
             __syncwarp();
         }
@@ -1010,6 +1037,15 @@ __global__ void __launch_bounds__(TC_THREADS) wgrad_tc_kernel(const __grid_const
             for (int i = 0; i < 16; i += 4)
                 *reinterpret_cast<uint4*>(dst + c0 + i) = make_uint4(r[i], r[i + 1], r[i + 2], r[i + 3]);
         }
+        if (do_bias) {
+            uint32_t r[16];
+            // this CTA ran a bias MMA iff one of its K-steps k in [s_beg*4, s_end*4) has k % ngrp == grp
+            const int k0 = s_beg * (WG_KQ / 16), k1 = s_end * (WG_KQ / 16);
+            const int first = k0 + ((grp - k0 % ngrp) % ngrp + ngrp) % ngrp;
+            if (nst > 0 && first < k1) { tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + bias_col, r); tmem_ld_wait(); }
+            else r[0] = 0u;
+            p.ws_bias[(((size_t)split * ngrp + grp) * p.m_tiles + mtile) * 128 + qd * 32 + lane] = __uint_as_float(r[0]);
+        }
         tc_fence_before();
     }
     __syncthreads();
@@ -1031,6 +1067,13 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restr
         float acc = 0.f;
         for (int s = 0; s < splits; ++s) acc += ws[off + s * stride];
         dw[((size_t)co * p.CinV + ci) * taps + tap] += acc;
+    }
+    if (p.ws_bias && p.dbias) {
+        for (int co = blockIdx.x * blockDim.x + threadIdx.x; co < p.CoutV; co += gridDim.x * blockDim.x) {
+            float acc = 0.f;
+            for (int s = 0; s < splits * grps; ++s) acc += p.ws_bias[((size_t)s * p.m_tiles + (co >> 7)) * 128 + (co & 127)];
+            p.dbias[co] += acc;
+        }
     }
 }
 
@@ -1057,7 +1100,7 @@ static void wg_plan(const ddpm_wgrad_args* a, WgTcParams* p, int* splits) {
     p->stages_total = (p->Qtot + WG_KQ - 1) / WG_KQ;
     p->nblkA = (p->NT + 63) / 64;
     p->stage_bytes = 2 * WG_KQ * 128 + p->nblkA * WG_ROWS * 128;
-    p->tmem_cols = 32; while (p->tmem_cols < p->ntap * p->NT) p->tmem_cols <<= 1;
+    p->tmem_cols = 32; while (p->tmem_cols < p->ntap * p->NT + 16) p->tmem_cols <<= 1;
     int yz = p->ntap * p->n_tiles * p->m_tiles;
     // one CTA per SM (176 KB of shared memory): the grid must not exceed ONE wave, or the second,
     // nearly empty wave doubles the kernel's duration -> floor, not ceil
@@ -1072,7 +1115,7 @@ static void wg_plan(const ddpm_wgrad_args* a, WgTcParams* p, int* splits) {
 extern "C" int64_t ddpm_wgrad_workspace_bytes(const ddpm_wgrad_args* a) {
     if (!a || !wgrad_tc_supported(a)) return 0;
     WgTcParams p; int splits; wg_plan(a, &p, &splits);
-    return (int64_t)splits * p.m_tiles * p.ntap * p.n_tiles * 128 * p.ntap * p.NT * 4;
+    return (int64_t)splits * p.m_tiles * p.ntap * p.n_tiles * 128 * p.ntap * p.NT * 4 + (int64_t)splits * p.ntap * p.n_tiles * p.m_tiles * 128 * 4;
 }
 
 int wgrad_tc_supported(const ddpm_wgrad_args* a) {
@@ -1090,9 +1133,12 @@ int wgrad_tc_supported(const ddpm_wgrad_args* a) {
 int wgrad_tc_launch(const ddpm_wgrad_args* a, cudaStream_t st) {
     int rc = get_encode(); if (rc) return rc;
     WgTcParams p; int splits; wg_plan(a, &p, &splits);
-    int64_t need = (int64_t)splits * p.m_tiles * p.ntap * p.n_tiles * 128 * p.ntap * p.NT * 4;
+    const int64_t main_bytes = (int64_t)splits * p.m_tiles * p.ntap * p.n_tiles * 128 * p.ntap * p.NT * 4;
+    int64_t need = main_bytes + (int64_t)splits * p.ntap * p.n_tiles * p.m_tiles * 128 * 4;
     if (!a->workspace || a->workspace_bytes < need) return DDPM_E_ARG;
     p.ws = (float*)a->workspace;
+    p.dbias = a->dbias;
+    p.ws_bias = a->dbias ? (float*)((char*)a->workspace + main_bytes) : nullptr;
     CUtensorMap tmY, tmA;
     {
         uint64_t d[2] = {(uint64_t)p.Cout, (uint64_t)p.Qtot}; uint64_t s[1] = {(uint64_t)a->dy.pitch * 2};
@@ -1104,7 +1150,7 @@ int wgrad_tc_launch(const ddpm_wgrad_args* a, cudaStream_t st) {
         uint32_t b[2] = {64, WG_ROWS};
         if (encode(&tmA, a->act.ptr, 2, d, s, b, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
     }
-    size_t smem = (size_t)WG_STAGES * p.stage_bytes + 8 * (2 * WG_STAGES + 1) + 16 + 1024;
+    size_t smem = (size_t)WG_STAGES * p.stage_bytes + 2048 + 8 * (2 * WG_STAGES + 1) + 16 + 1024;
     static size_t configured = 0;
     if (smem > configured) {
         CUDA_TRY(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -251,10 +251,13 @@ def conv(E: Exec, x: Act, wpack: torch.Tensor, out: Act, k: int, stride: int = 1
 
 
 def wgrad(E: Exec, act: Act, dy: Act, w: torch.nn.Parameter, k: int, stride: int = 1, pad: int = 0,
-          a_silu: bool = False) -> None:
-    """dW += dY^T (*) act.  `act` / `dy` may carry zero-padded channels beyond the parameter's shape."""
+          a_silu: bool = False, bias: Optional[torch.nn.Parameter] = None) -> None:
+    """dW += dY^T (*) act (and db += sum_pixels dY when `bias` is given, from the same launch on the tensor-core
+    path).  `act` / `dy` may carry zero-padded channels beyond the parameter's shape."""
     g = grad_of(w)
     if g is None:
+        if bias is not None:
+            colsum(E, dy.slice(0, bias.numel()) if dy.C != bias.numel() else dy, None, bias)
         return
     a = _lib.WgradArgs()
     a.act, a.dy = act.desc(), dy.desc()
@@ -267,6 +270,7 @@ def wgrad(E: Exec, act: Act, dy: Act, w: torch.nn.Parameter, k: int, stride: int
     a.workspace, a.workspace_bytes = None, 0
     a.cin_valid = w.shape[1] if act.C != w.shape[1] else 0
     a.cout_valid = w.shape[0] if dy.C != w.shape[0] else 0
+    a.dbias = _gptr(bias)
     if E.use_tc and act.dt == _lib.BF16 and stride == 1:
         need = int(_lib.lib.ddpm_wgrad_workspace_bytes(C.byref(a)))
         if need > 0:
@@ -410,8 +414,7 @@ def resblock_bwd(E: Exec, blk, saved, dout: Act, dx: Optional[Act] = None, dx_ac
     x, st1, a1, h, st2, a2, p_drop, layer = saved
     has_skip_conv = isinstance(blk.skip, torch.nn.Conv2d)
     # conv2 (+ skip conv) parameter gradients
-    wgrad(E, a2, dout, blk.conv2.weight, 3, 1, 1)
-    colsum(E, dout, None, blk.conv2.bias)
+    wgrad(E, a2, dout, blk.conv2.weight, 3, 1, 1, bias=blk.conv2.bias)
     _, w2d = E.wcache.get(E, blk.conv2.weight, E.dt, True)
     da2 = conv(E, dout, w2d, E.act(x.N, x.H, x.W, blk.out_ch), 3, 1, 1)
     dtb = E.f32(x.N, blk.out_ch)
@@ -422,8 +425,7 @@ def resblock_bwd(E: Exec, blk, saved, dout: Act, dx: Optional[Act] = None, dx_ac
     _, w1d = E.wcache.get(E, blk.conv1.weight, E.dt, True)
     da1 = conv(E, dh, w1d, E.act(x.N, x.H, x.W, blk.in_ch), 3, 1, 1)
     if has_skip_conv:
-        wgrad(E, x, dout, blk.skip.weight, 1)
-        colsum(E, dout, None, blk.skip.bias)
+        wgrad(E, x, dout, blk.skip.weight, 1, bias=blk.skip.bias)
         _, wsd = E.wcache.get(E, blk.skip.weight, E.dt, True)
         if dx is None:
             dx, dx_accum = E.act(x.N, x.H, x.W, blk.in_ch), False
@@ -463,8 +465,7 @@ def attn_bwd(E: Exec, blk, saved, dout: Act, dx: Optional[Act] = None, dx_accum:
     heads, d = blk.num_heads, blk.head_dim
     inner = heads * d
     n_tok = x.H * x.W
-    wgrad(E, o, dout, blk.proj.weight, 1)
-    colsum(E, dout, None, blk.proj.bias)
+    wgrad(E, o, dout, blk.proj.weight, 1, bias=blk.proj.bias)
     _, wpd = E.wcache.get(E, blk.proj.weight, E.dt, True)
     do = conv(E, dout, wpd, E.act(x.N, x.H, x.W, inner), 1)
     dqkv = E.act(x.N, x.H, x.W, 3 * inner)
@@ -494,7 +495,6 @@ def down_fwd(E: Exec, mod, x: Act, out: Optional[Act] = None):
 
 def down_bwd(E: Exec, mod, saved, dout: Act, dx: Optional[Act], dx_accum: bool) -> Act:
     x = saved
-    colsum(E, dout, None, mod.conv.bias)
     _, wd = E.wcache.get(E, mod.conv.weight, E.dt, True)
     if dx is None:
         dx, dx_accum = E.act(x.N, x.H, x.W, x.C), False
@@ -502,10 +502,10 @@ def down_bwd(E: Exec, mod, saved, dout: Act, dx: Optional[Act], dx_accum: bool) 
         # stride-2 gradients as stride-1 tensor-core problems on the zero-interleaved dY
         up = E.act(x.N, x.H, x.W, dout.C)
         _lib.call("ddpm_zero_upsample2x", C.byref(dout.desc()), C.byref(up.desc()), E.dt, E.stream)
-        wgrad(E, x, up, mod.conv.weight, 3, 1, 1)
+        wgrad(E, x, up, mod.conv.weight, 3, 1, 1, bias=mod.conv.bias)        # zeros of `up` add nothing to the bias sum
         conv(E, up, wd, dx, 3, 1, 1, accum=dx_accum)
     else:
-        wgrad(E, x, dout, mod.conv.weight, 3, 2, 1)
+        wgrad(E, x, dout, mod.conv.weight, 3, 2, 1, bias=mod.conv.bias)
         conv(E, dout, wd, dx, 3, 2, 1, accum=dx_accum, mode=_lib.CONV_TRANSPOSED)
     return dx
 
@@ -522,8 +522,7 @@ def up_fwd(E: Exec, mod, x: Act, out: Optional[Act] = None):
 
 def up_bwd(E: Exec, mod, saved, dout: Act, dx: Optional[Act] = None, dx_accum: bool = False) -> Act:
     u = saved
-    wgrad(E, u, dout, mod.conv.weight, 3, 1, 1)
-    colsum(E, dout, None, mod.conv.bias)
+    wgrad(E, u, dout, mod.conv.weight, 3, 1, 1, bias=mod.conv.bias)
     _, wd = E.wcache.get(E, mod.conv.weight, E.dt, True)
     du = conv(E, dout, wd, E.act(u.N, u.H, u.W, u.C), 3, 1, 1)
     if dx is None:
@@ -705,8 +704,7 @@ def unet_backward(E: Exec, model, saved, dy: torch.Tensor, need_dx: bool, progre
     cpad = 16 if E.use_tc else 0
     oc = model.out_conv.out_channels
     dyn = to_nhwc(E, dy, cpad=cpad)
-    wgrad(E, a, dyn, model.out_conv.weight, 3, 1, 1)
-    colsum(E, dyn.slice(0, oc) if dyn.C != oc else dyn, None, model.out_conv.bias)
+    wgrad(E, a, dyn, model.out_conv.weight, 3, 1, 1, bias=model.out_conv.bias)
     _, wd = E.wcache.get(E, model.out_conv.weight, E.dt, True, cout_pad=cpad)
     da = conv(E, dyn, wd, E.act(a.N, a.H, a.W, a.C), 3, 1, 1)
     dcur = gn_bwd(E, cur_h, st, model.out_norm, 1, 0.0, 0, da, da, False, dy_scratch=True)
@@ -757,8 +755,7 @@ def unet_backward(E: Exec, model, saved, dy: torch.Tensor, need_dx: bool, progre
                 dcur = add(E, dcur, tgt, tgt)
         elif kind == "in":
             x_in = ent[1]
-            wgrad(E, x_in, dcur, model.in_conv.weight, 3, 1, 1)
-            colsum(E, dcur, None, model.in_conv.bias)
+            wgrad(E, x_in, dcur, model.in_conv.weight, 3, 1, 1, bias=model.in_conv.bias)
             if need_dx:
                 _, wdi = E.wcache.get(E, model.in_conv.weight, E.dt, True, cin_pad=cpad)
                 dxa = conv(E, dcur, wdi, E.act(x_in.N, x_in.H, x_in.W, x_in.C), 3, 1, 1)

@@ -177,6 +177,8 @@ typedef struct {
     void* workspace;          /* split-K partials for the tensor-core kernel (may be NULL -> CUDA cores) */
     int64_t workspace_bytes;
     int32_t cin_valid, cout_valid; /* >0: act / dy carry zero-padded channels; dw is [cout_valid][cin_valid][KH][KW] */
+    float* dbias;             /* fp32 [cout_valid or dy.C], accumulated with sum over pixels of dy (conv bias gradient); may be NULL.
+                               * The tensor-core kernel gets it from one extra N=16 MMA per K-step against a tile of ones. */
 } ddpm_wgrad_args;
 int ddpm_conv_wgrad(const ddpm_wgrad_args* a, void* stream);
 /* bytes of workspace the tensor-core wgrad wants for this problem (0: it will not be used) */

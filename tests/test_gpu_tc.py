@@ -79,13 +79,19 @@ def test_wgrad_tc_matches_simt(mods, case):
     co_v = 3 if Co == 16 else Co
     w1 = torch.nn.Parameter(torch.zeros(co_v, ci_v, k, k, device=dev()))
     w2 = torch.nn.Parameter(torch.zeros(co_v, ci_v, k, k, device=dev()))
+    b1 = torch.nn.Parameter(torch.zeros(co_v, device=dev()))
+    b2 = torch.nn.Parameter(torch.zeros(co_v, device=dev()))
     _lib.lib.ddpm_set_force_simt(1)
-    engine.wgrad(E, x, dy, w1, k, 1, k // 2)
+    engine.wgrad(E, x, dy, w1, k, 1, k // 2, bias=b1)
     _lib.lib.ddpm_set_force_simt(0)
-    engine.wgrad(E, x, dy, w2, k, 1, k // 2)
-    engine.wgrad(E, x, dy, w2, k, 1, k // 2)          # accumulates
+    engine.wgrad(E, x, dy, w2, k, 1, k // 2, bias=b2)
+    engine.wgrad(E, x, dy, w2, k, 1, k // 2, bias=b2)          # accumulates
     torch.cuda.synchronize()
     assert relerr(w2.grad / 2, w1.grad) < 1e-2
+    # bias gradient: the ones-operand MMA of the tensor-core kernel vs the column-sum kernel vs torch
+    ref_b = dy.interior().float().sum((0, 1, 2))[:co_v]
+    assert relerr(b1.grad, ref_b) < 1e-3
+    assert relerr(b2.grad / 2, ref_b) < 1e-3
 
 
 def test_downsample_grads_via_zero_upsample(mods):

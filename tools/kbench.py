@@ -117,6 +117,9 @@ if "wgrad" in only:
         fl = 2.0 * B * hw * hw * co * ci * 9
         sec = timeit(lambda: engine.wgrad(E, x, dy, w, 3, 1, 1))
         report("wgrad", f"{ci}->{co}@{hw}", sec, flops=fl, cnt=cnt)
+        bpar = torch.nn.Parameter(torch.zeros(co, device=dev))
+        sec = timeit(lambda: engine.wgrad(E, x, dy, w, 3, 1, 1, bias=bpar))
+        report("wgrad", f"{ci}->{co}@{hw} skip(+bias grad)", sec, flops=fl, cnt=cnt)
         del x, dy
 
 if "gn" in only:
