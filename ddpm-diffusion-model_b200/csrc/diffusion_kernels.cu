@@ -250,10 +250,17 @@ extern "C" int ddpm_mse_bwd(const void* pred, int pred_dtype, const float* noise
 
 // ---------------------------------------------------------------- x0_hat helpers
 // x0_hat = (x_t - sqrt(1-ab) eps) / (sqrt(ab) + 1e-12), then dynamic threshold or clamp.
-struct X0Coef { float sa_eps, so, thr_div; int flags; };
+// a / b for a per-sample constant b with r = 1/b precomputed (IEEE) once per block: one Newton step on the
+// quotient, 3 FP32 instructions, within 1 ulp of the correctly rounded quotient (IEEE division is ~12
+// instructions and made the DDIM step instruction-bound: 67 % of HBM peak at eta = 0).
+__device__ __forceinline__ float div_const(float a, float b, float r) {
+    const float q = a * r;
+    return fmaf(fmaf(-b, q, a), r, q);
+}
+struct X0Coef { float sa_eps, so, thr_div, r_sa, r_thr; int flags; };
 __device__ __forceinline__ float x0_hat(const X0Coef& c, float x, float e) {
-    float v = __fdiv_rn(__fsub_rn(x, __fmul_rn(c.so, e)), c.sa_eps);
-    if (c.flags & DDPM_DYN_THRESH) { v = __fdiv_rn(v, c.thr_div); v = fminf(fmaxf(v, -1.f), 1.f); }
+    float v = div_const(__fsub_rn(x, __fmul_rn(c.so, e)), c.sa_eps, c.r_sa);
+    if (c.flags & DDPM_DYN_THRESH) { v = div_const(v, c.thr_div, c.r_thr); v = fminf(fmaxf(v, -1.f), 1.f); }
     else if (c.flags & DDPM_CLAMP_X0) v = fminf(fmaxf(v, -1.f), 1.f);
     return v;
 }
@@ -265,6 +272,7 @@ template <bool CONST> __device__ __forceinline__ X0Coef make_x0coef(const float*
     c.flags = flags;
     c.thr_div = 1.f;
     if (flags & DDPM_DYN_THRESH) c.thr_div = fmaxf(fmaxf(amax[b], 1.0f), dyn_s);
+    c.r_sa = __fdiv_rn(1.0f, c.sa_eps); c.r_thr = __fdiv_rn(1.0f, c.thr_div);
     return c;
 }
 
@@ -363,7 +371,7 @@ extern "C" int ddpm_p_sample_step(void* sched, const float* xt, const void* eps,
 template <typename TE, bool CONST> struct DdimStep {
     const float* xt; const TE* eps; const float* noise; const int64_t* t; const int64_t* tp; float eta;
     const float* amax; float dyn_s; int flags; float* out; const float* g; int T;
-    struct Coef { X0Coef x; float sq_at, inv_dir, sq_ap, add, sigma; };
+    struct Coef { X0Coef x; float sq_at, inv_dir, r_dir, sq_ap, add, sigma; };
     __device__ Coef coef(int b) const {
         int tt = clamp_t(t[b], T), tq = clamp_t(tp[b], T);
         Coef c;
@@ -371,7 +379,8 @@ template <typename TE, bool CONST> struct DdimStep {
         float a_t = tab<CONST>(g, T, 2, tt), a_p = tab<CONST>(g, T, 2, tq);
         float om = __fadd_rn(__fsub_rn(1.0f, a_t), 1e-12f);
         c.sq_at = sqrtf(a_t);
-        c.inv_dir = sqrtf(om);                                          // divide by it (IEEE), not multiply
+        c.inv_dir = sqrtf(om);                                          // divide by it (div_const), not multiply by 1/x
+        c.r_dir = __fdiv_rn(1.0f, c.inv_dir);
         float s1 = sqrtf(__fdiv_rn(__fsub_rn(1.0f, a_p), om));
         float s2 = sqrtf(__fsub_rn(1.0f, __fdiv_rn(a_t, __fadd_rn(a_p, 1e-12f))));
         c.sigma = __fmul_rn(__fmul_rn(eta, s1), s2);
@@ -381,7 +390,7 @@ template <typename TE, bool CONST> struct DdimStep {
     }
     __device__ __forceinline__ float f(const Coef& c, float x, float e, float z) const {
         float x0 = x0_hat(c.x, x, e);
-        float dir = __fdiv_rn(__fsub_rn(x, __fmul_rn(c.sq_at, x0)), c.inv_dir);
+        float dir = div_const(__fsub_rn(x, __fmul_rn(c.sq_at, x0)), c.inv_dir, c.r_dir);
         float r = __fadd_rn(__fmul_rn(c.sq_ap, x0), __fmul_rn(c.add, dir));
         return __fadd_rn(r, __fmul_rn(c.sigma, z));
     }
