@@ -40,6 +40,12 @@ class WgradArgs(C.Structure):
                 ("dbias", C.c_void_p)]
 
 
+class PackEntry(C.Structure):
+    """struct ddpm_pack_entry"""
+    _fields_ = [("w", C.c_void_p), ("wf", C.c_void_p), ("wd", C.c_void_p), ("Cout", C.c_int32), ("Cin", C.c_int32),
+                ("taps", C.c_int32), ("CiP", C.c_int32), ("CoP", C.c_int32), ("dtype", C.c_int32)]
+
+
 class AdamHyper(C.Structure):
     """struct ddpm_adam_hyper"""
     _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
@@ -81,6 +87,7 @@ SIGNATURES = {
     "ddpm_conv_wgrad": [C.POINTER(WgradArgs), _vp],
     "ddpm_wgrad_workspace_bytes": [C.POINTER(WgradArgs)],
     "ddpm_pack_weights": [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp],
+    "ddpm_pack_weights_batched": [_vp, _i, _vp],
     "ddpm_attn_fwd": [_TP, _TP, _i, _i, _vp, _i, _vp],
     "ddpm_attn_bwd": [_TP, _TP, _TP, _vp, _TP, _i, _i, _vp, _i, _vp],
     "ddpm_param_reduce": [_vp, _i64, _vp, _vp],

@@ -134,9 +134,37 @@ class WeightCache:
     def __init__(self):
         self.entries: Dict[tuple, tuple] = {}
         self.epoch = 0
+        self._table = None            # (device uint8 tensor of ddpm_pack_entry[], n, signature)
 
     def bump(self):
         self.epoch += 1
+
+    def repack_all(self, stream: int) -> bool:
+        """After an in-place optimiser step every packed copy is stale at once: refresh all live entries with ONE
+        launch (ddpm_pack_weights_batched) instead of one launch per weight on the next forward.  Returns False
+        (and leaves the lazy per-weight path to do it) if nothing is cached yet."""
+        self.epoch += 1
+        live = [(k, e) for k, e in self.entries.items()
+                if e[4]() is not None and e[3].data_ptr() == e[4]().data_ptr() and e[4]().is_cuda]
+        if not live:
+            return False
+        sig = tuple((k, e[3].data_ptr(), e[1].data_ptr(), e[2].data_ptr() if e[2] is not None else 0) for k, e in live)
+        if self._table is None or self._table[2] != sig:
+            arr = (_lib.PackEntry * len(live))()
+            for i, (k, e) in enumerate(live):
+                _, dt, cin_pad, cout_pad = k
+                wd = e[3]
+                co, ci = wd.shape[0], wd.shape[1]
+                taps = wd.shape[2] * wd.shape[3] if wd.dim() == 4 else 1
+                arr[i] = _lib.PackEntry(wd.data_ptr(), e[1].data_ptr(), e[2].data_ptr() if e[2] is not None else None,
+                                        co, ci, taps, max(ci, cin_pad), max(co, cout_pad), dt)
+            host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+            self._table = (host.to(live[0][1][1].device), len(live), sig)
+        _lib.call("ddpm_pack_weights_batched", self._table[0].data_ptr(), self._table[1], stream)
+        for k, e in live:
+            w = e[4]()
+            self.entries[k] = ((w._version, self.epoch, w.data_ptr()), e[1], e[2], e[3], e[4])
+        return True
 
     def get(self, E: "Exec", w: torch.Tensor, dt: int, need_dgrad: bool, cin_pad: int = 0, cout_pad: int = 0):
         key = (id(w), dt, cin_pad, cout_pad)

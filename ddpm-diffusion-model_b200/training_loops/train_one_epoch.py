@@ -93,7 +93,7 @@ class FusedStep:
             _lib.call("ddpm_scaler_update", scaler._scale.data_ptr(), scaler._growth_tracker.data_ptr(),
                       self.stats.data_ptr(), float(scaler.get_growth_factor()), float(scaler.get_backoff_factor()),
                       int(scaler.get_growth_interval()), st)
-        GLOBAL_WCACHE.bump()              # packed weight copies are stale now
+        GLOBAL_WCACHE.repack_all(st)      # packed weight copies are stale now: one batched launch refreshes them all
         ar.grad.zero_()                   # == optimizer.zero_grad(); grads stay attached (views)
 
     def grad_norm(self, scaler, use_scaler: bool) -> float:

@@ -189,6 +189,15 @@ int64_t ddpm_wgrad_workspace_bytes(const ddpm_wgrad_args* a);
 int ddpm_pack_weights(const float* w, int Cout, int Cin, int KH, int KW, void* w_fwd, void* w_dgrad,
                       int dtype, int cin_pad, int cout_pad, void* stream);
 
+/* the same for many weights in one launch; `entries_dev` is an array in DEVICE memory */
+typedef struct {
+    const float* w;      /* fp32 OIHW source */
+    void* wf;            /* packed fprop copy or NULL */
+    void* wd;            /* packed dgrad copy or NULL */
+    int32_t Cout, Cin, taps, CiP, CoP, dtype;
+} ddpm_pack_entry;
+int ddpm_pack_weights_batched(const ddpm_pack_entry* entries_dev, int n, void* stream);
+
 /* ---------------- attention: attention.py:56-74 -------------------------------------------- */
 /* qkv: NHWC with channel = s*heads*d + head*d + i (s in q,k,v) -- the layout conv `qkv` emits, so
  * the four permute+contiguous copies (:63-65,72) disappear.  lse: fp32 [N][heads][H*W]. */
