@@ -235,6 +235,42 @@ class Exec:
         return Act.wrap(t, B, 1, 1, Cn, _lib.F32, 0)
 
 
+_SIDE_STREAMS: Dict[str, "torch.cuda.Stream"] = {}
+
+
+def overlap_enabled() -> bool:
+    import os
+    return os.environ.get("DDPM_B200_WGRAD_OVERLAP", "1") != "0"
+
+
+def _event_on(stream) -> "torch.cuda.Event":
+    ev = torch.cuda.Event()
+    ev.record(stream)
+    return ev
+
+
+def wgrad_async(E: "Exec", after: "torch.cuda.Event", fn) -> "torch.cuda.Event":
+    """Run `fn` (weight-gradient launches) on the per-device side stream once `after` (a main-stream event) has
+    completed; returns the side-stream event that marks their completion.  The weight gradients are off the
+    critical path of backward (only the optimiser needs them), and the tensor-core wgrad kernel (TMA + MMA, one
+    178 KB CTA per SM) leaves the ALU/LSU and two CTA slots per SM free -- exactly what the issue-bound
+    GroupNorm backward running next on the main stream needs."""
+    key = str(E.device)
+    side = _SIDE_STREAMS.get(key)
+    if side is None:
+        # high priority: when a wgrad and a GroupNorm backward become runnable at the same moment the 178 KB wgrad
+        # CTAs must be placed first -- GroupNorm CTAs then still fit two per SM next to them, the other order does
+        # not (three resident GroupNorm CTAs hold 61 K of the SM's 64 K registers)
+        side = _SIDE_STREAMS[key] = torch.cuda.Stream(E.device, priority=-1)
+    side.wait_event(after)
+    main_handle, E.stream = E.stream, side.cuda_stream
+    try:
+        fn()
+    finally:
+        E.stream = main_handle
+    return _event_on(side)
+
+
 def grad_of(p: torch.nn.Parameter) -> Optional[torch.Tensor]:
     """fp32 gradient buffer of a parameter (created zeroed on first use; kernels accumulate)."""
     if not p.requires_grad:
@@ -441,6 +477,8 @@ def resblock_bwd(E: Exec, blk, saved, dout: Act, dx: Optional[Act] = None, dx_ac
     is the identity and no explicit target is given)."""
     x, st1, a1, h, st2, a2, p_drop, layer = saved
     has_skip_conv = isinstance(blk.skip, torch.nn.Conv2d)
+    if E.use_tc and overlap_enabled():
+        return _resblock_bwd_overlapped(E, blk, saved, dout, dx, dx_accum)
     # conv2 (+ skip conv) parameter gradients
     wgrad(E, a2, dout, blk.conv2.weight, 3, 1, 1, bias=blk.conv2.bias)
     _, w2d = E.wcache.get(E, blk.conv2.weight, E.dt, True)
@@ -465,6 +503,52 @@ def resblock_bwd(E: Exec, blk, saved, dout: Act, dx: Optional[Act] = None, dx_ac
         else:
             gn_bwd(E, x, st1, blk.norm1, 1, 0.0, 0, da1, dx, dx_accum, dy_scratch=True)
             add(E, dx, dout, dx)
+    return dx, dtb
+
+
+def _resblock_bwd_overlapped(E: Exec, blk, saved, dout: Act, dx: Optional[Act], dx_accum: bool):
+    """Same arithmetic as the serial path; the three weight-gradient launches run on the side stream, each paired
+    with the GroupNorm backward that follows on the main stream:
+        main:  dgrad(conv2) | gn_bwd(norm2) | dgrad(conv1) [skip dgrad] | gn_bwd(norm1)
+        side:               | wgrad(conv2)[,skip]          |            | wgrad(conv1)
+    Hazards: wgrad(conv2/skip) read `dout`, which gn_bwd(norm1) overwrites -> main waits for them first; wgrad(conv1)
+    reads dh / a1, which go back to the buffer pool when this function returns -> main waits before returning."""
+    x, st1, a1, h, st2, a2, p_drop, layer = saved
+    has_skip_conv = isinstance(blk.skip, torch.nn.Conv2d)
+    main = torch.cuda.current_stream(E.device)
+    # gradient buffers that do not exist yet are created (zero-filled) on the MAIN stream, before the fork events
+    for prm in (blk.conv2.weight, blk.conv2.bias, blk.conv1.weight) + ((blk.skip.weight, blk.skip.bias) if has_skip_conv else ()):
+        if prm is not None:
+            grad_of(prm)
+    _, w2d = E.wcache.get(E, blk.conv2.weight, E.dt, True)
+    da2 = conv(E, dout, w2d, E.act(x.N, x.H, x.W, blk.out_ch), 3, 1, 1)
+
+    def side1():
+        wgrad(E, a2, dout, blk.conv2.weight, 3, 1, 1, bias=blk.conv2.bias)
+        if has_skip_conv:
+            wgrad(E, x, dout, blk.skip.weight, 1, bias=blk.skip.bias)
+    s1 = wgrad_async(E, _event_on(main), side1)
+    dtb = E.f32(x.N, blk.out_ch)
+    dh = gn_bwd(E, h, st2, blk.norm2, 1, p_drop, layer, da2, da2, False, colsum_nc=dtb, colsum_bias=blk.conv1.bias,
+                dy_scratch=True)
+    _, w1d = E.wcache.get(E, blk.conv1.weight, E.dt, True)
+    da1 = conv(E, dh, w1d, E.act(x.N, x.H, x.W, blk.in_ch), 3, 1, 1)
+    if has_skip_conv:
+        _, wsd = E.wcache.get(E, blk.skip.weight, E.dt, True)
+        if dx is None:
+            dx, dx_accum = E.act(x.N, x.H, x.W, blk.in_ch), False
+        conv(E, dout, wsd, dx, 1, accum=dx_accum)
+    s2 = wgrad_async(E, _event_on(main), lambda: wgrad(E, a1, dh, blk.conv1.weight, 3, 1, 1))
+    main.wait_event(s1)                                   # dout is about to be overwritten / handed on
+    if has_skip_conv:
+        gn_bwd(E, x, st1, blk.norm1, 1, 0.0, 0, da1, dx, True, dy_scratch=True)
+    else:
+        if dx is None:
+            dx = gn_bwd(E, x, st1, blk.norm1, 1, 0.0, 0, da1, dout, True, dy_scratch=True)       # dout += gn_bwd -> dx
+        else:
+            gn_bwd(E, x, st1, blk.norm1, 1, 0.0, 0, da1, dx, dx_accum, dy_scratch=True)
+            add(E, dx, dout, dx)
+    main.wait_event(s2)                                   # dh / a1 / a2 are recycled by the caller from here on
     return dx, dtb
 
 
