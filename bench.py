@@ -125,7 +125,7 @@ def run_reference(args):
                          "sample": f"{steps} optimiser steps at B=8, 64x64, fp32, dropout off"},
         "e2e": {"value": ips, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    GUARD.emit(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -326,12 +326,31 @@ def run_ours(args):
             "loss": last[0] if last else None, "pool_misses_in_timed_region": pool_misses, "ddim100": ddim,
             "train_tflops_per_gpu": gf_train * 1e9 * B * args.steps / sec / 1e12,
         }
-        print(json.dumps(line), flush=True)
+        GUARD.emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
+class _StdoutGuard:
+    """Everything written to fd 1 while the benchmark runs (NCCL's version banner, sampler progress prints, library
+    chatter) goes to stderr; only `emit()` reaches the real stdout -> exactly ONE JSON line."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line: str):
+        sys.stdout.flush()
+        os.write(self.real, (line + "\n").encode())
+
+
+GUARD = None
+
+
 def main():
+    global GUARD
+    GUARD = _StdoutGuard()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
