@@ -46,6 +46,11 @@ class PackEntry(C.Structure):
                 ("taps", C.c_int32), ("CiP", C.c_int32), ("CoP", C.c_int32), ("dtype", C.c_int32)]
 
 
+class LinEntry(C.Structure):
+    """struct ddpm_lin_entry"""
+    _fields_ = [("w", C.c_void_p), ("bias", C.c_void_p), ("N", C.c_int32), ("col0", C.c_int32)]
+
+
 class AdamHyper(C.Structure):
     """struct ddpm_adam_hyper"""
     _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
@@ -88,6 +93,8 @@ SIGNATURES = {
     "ddpm_wgrad_workspace_bytes": [C.POINTER(WgradArgs)],
     "ddpm_pack_weights": [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp],
     "ddpm_pack_weights_batched": [_vp, _i, _vp],
+    "ddpm_linear_grouped_fwd": [_vp, _i, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp],
+    "ddpm_time_proj_bwd": [_vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _vp],
     "ddpm_attn_fwd": [_TP, _TP, _i, _i, _vp, _i, _vp],
     "ddpm_attn_bwd": [_TP, _TP, _TP, _vp, _TP, _i, _i, _vp, _i, _vp],
     "ddpm_param_reduce": [_vp, _i64, _vp, _vp],

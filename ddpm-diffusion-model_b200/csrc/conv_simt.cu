@@ -276,6 +276,122 @@ static int linear_small_launch(const ddpm_conv_args* a, cudaStream_t st) {
     return 0;
 }
 
+// ------------------------------------------------------------------------------------ time path, batched
+// All `time_proj` linears of the UNet (unet_backbone.py:27; 14 / 27 of them, same input silu(temb)) in ONE launch,
+// and the whole backward of one of them (dW, db and the accumulated d temb) in ONE launch instead of three.
+// 32x32 output tiles, inner tiles of 32, operands fetched through small functors so the same tile routine serves
+// row-major and transposed accesses.
+template <typename FA, typename FB>
+__device__ __forceinline__ void tile_gemm32(FA fa, FB fb, int Kin, float acc[2][2], float (*As)[LBM + 1], float (*Bs)[LBN + 1]) {
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    for (int k0 = 0; k0 < Kin; k0 += LBK) {
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {                       // 1024 elements per operand tile, 256 threads
+            const int l = tid + j * 256;
+            As[l >> 5][l & 31] = fa(l & 31, k0 + (l >> 5));  // (row, k): consecutive threads -> consecutive rows
+            Bs[l >> 5][l & 31] = fb(l & 31, k0 + (l >> 5));
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < LBK; ++kk) {
+            const float a0 = As[kk][ty * 2], a1 = As[kk][ty * 2 + 1];
+            const float b0 = Bs[kk][tx * 2], b1 = Bs[kk][tx * 2 + 1];
+            acc[0][0] = fmaf(a0, b0, acc[0][0]); acc[0][1] = fmaf(a0, b1, acc[0][1]);
+            acc[1][0] = fmaf(a1, b0, acc[1][0]); acc[1][1] = fmaf(a1, b1, acc[1][1]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) linear_grouped_fwd_kernel(const float* __restrict__ x, int M, int K, int xpitch,
+                                                                 const ddpm_lin_entry* __restrict__ entries, float* out, int opitch, int a_silu) {
+    __shared__ float As[LBK][LBM + 1];
+    __shared__ float Bs[LBK][LBN + 1];
+    const ddpm_lin_entry e = entries[blockIdx.z];
+    const int m0 = blockIdx.x * LBM, n0 = blockIdx.y * LBN;
+    if (n0 >= e.N) return;
+    const float* __restrict__ w = e.w;
+    float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+    // x is read k-fastest per row in global memory; the tile loader walks rows fastest -> strided, but the whole
+    // operand (B x 512 fp32 = 256 KB) is L1/L2 resident and shared by every block
+    tile_gemm32([&](int r, int k) { const int m = m0 + r; float v = (m < M && k < K) ? x[(int64_t)m * xpitch + k] : 0.f; return a_silu ? silu_f(v) : v; },
+                [&](int r, int k) { const int n = n0 + r; return (n < e.N && k < K) ? __ldg(w + (int64_t)n * K + k) : 0.f; },
+                K, acc, As, Bs);
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int m = m0 + ty * 2 + i, n = n0 + tx * 2 + j;
+            if (m < M && n < e.N) out[(int64_t)m * opitch + e.col0 + n] = acc[i][j] + (e.bias ? e.bias[n] : 0.f);
+        }
+}
+
+extern "C" int ddpm_linear_grouped_fwd(const float* x, int M, int K, int xpitch, const ddpm_lin_entry* entries_dev, int n,
+                                       int max_N, float* out, int out_pitch, int a_silu, void* stream) {
+    if (!x || !entries_dev || !out || M <= 0 || K <= 0 || n <= 0 || max_N <= 0) return DDPM_E_ARG;
+    dim3 grid(ceil_div(M, LBM), ceil_div(max_N, LBN), n);
+    linear_grouped_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, M, K, xpitch, entries_dev, out, out_pitch, a_silu);
+    LAUNCH_OK();
+    return 0;
+}
+
+// y = W silu(temb) + b for one block.  Given dy = dtb [B][N]:  dW[n][k] += sum_b dy[b][n] silu(temb[b][k]),
+// db[n] += sum_b dy[b][n],  dtemb[b][k] (+)= (sum_n dy[b][n] W[n][k]) * silu'(temb[b][k]).
+__global__ void __launch_bounds__(256) time_proj_bwd_kernel(const float* __restrict__ temb, int B, int K, const float* __restrict__ dy,
+                                                            int dpitch, int N, const float* __restrict__ w, float* dw, float* db,
+                                                            float* dtemb, int accum, int tilesA_n) {
+    __shared__ float As[LBK][LBM + 1];
+    __shared__ float Bs[LBK][LBN + 1];
+    const int kt = blockIdx.x, r = blockIdx.y;               // K tile; row tile of part A (n) or part B (b)
+    const int k0 = kt * LBN;
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+    if (r < tilesA_n) {                                      // ---- part A: weight (and bias) gradient, inner dim = batch
+        const int n0 = r * LBM;
+        tile_gemm32([&](int rr, int b) { const int n = n0 + rr; return (n < N && b < B) ? dy[(int64_t)b * dpitch + n] : 0.f; },
+                    [&](int rr, int b) { const int k = k0 + rr; return (k < K && b < B) ? silu_f(temb[(int64_t)b * K + k]) : 0.f; },
+                    B, acc, As, Bs);
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int n = n0 + ty * 2 + i, k = k0 + tx * 2 + j;
+                if (n < N && k < K) dw[(int64_t)n * K + k] += acc[i][j];
+            }
+        if (kt == 0 && db && threadIdx.x < LBM) {
+            const int n = n0 + threadIdx.x;
+            if (n < N) { float s = 0.f; for (int b = 0; b < B; ++b) s += dy[(int64_t)b * dpitch + n]; db[n] += s; }
+        }
+    } else {                                                 // ---- part B: d temb, inner dim = N
+        const int b0 = (r - tilesA_n) * LBM;
+        tile_gemm32([&](int rr, int n) { const int b = b0 + rr; return (b < B && n < N) ? dy[(int64_t)b * dpitch + n] : 0.f; },
+                    [&](int rr, int n) { const int k = k0 + rr; return (k < K && n < N) ? __ldg(w + (int64_t)n * K + k) : 0.f; },
+                    N, acc, As, Bs);
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int b = b0 + ty * 2 + i, k = k0 + tx * 2 + j;
+                if (b < B && k < K) {
+                    const float v = acc[i][j] * dsilu_f(temb[(int64_t)b * K + k]);
+                    float* o = dtemb + (int64_t)b * K + k;
+                    *o = accum ? *o + v : v;
+                }
+            }
+    }
+}
+
+extern "C" int ddpm_time_proj_bwd(const float* temb, int B, int K, const float* dy, int dy_pitch, int N, const float* w,
+                                  float* dw, float* db, float* dtemb, int accum_dtemb, void* stream) {
+    if (!temb || !dy || !w || !dw || !dtemb || B <= 0 || K <= 0 || N <= 0) return DDPM_E_ARG;
+    const int tilesA = ceil_div(N, LBM), tilesB = ceil_div(B, LBM);
+    dim3 grid(ceil_div(K, LBN), tilesA + tilesB);
+    time_proj_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(temb, B, K, dy, dy_pitch, N, w, dw, db, dtemb, accum_dtemb, tilesA);
+    LAUNCH_OK();
+    return 0;
+}
+
 int conv_simt_launch(const ddpm_conv_args* a, cudaStream_t st) {
     if (linear_small_ok(a)) return linear_small_launch(a, st);
     ConvP p;

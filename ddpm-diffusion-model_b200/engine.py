@@ -448,6 +448,44 @@ def linear_bwd(E: Exec, x: torch.Tensor, lin: torch.nn.Linear, a_silu: bool, dy:
     return dx
 
 
+def time_proj_all_fwd(E: Exec, model, rbs: list, temb: torch.Tensor) -> List[torch.Tensor]:
+    """Per-block time biases `time_proj(temb)` (unet_backbone.py:25-27,41) for every ResBlock with ONE launch; returns
+    column-slice views [B][C_i] of one [B][sum C_i] buffer (the convolution epilogue takes a row pitch)."""
+    lins = [b.time_proj[1] for b in rbs]
+    sig = tuple((l.weight.data_ptr(), l.bias.data_ptr() if l.bias is not None else 0) for l in lins)
+    tab = getattr(model, "_ddpm_tp_table", None)
+    if tab is None or tab[0] != sig or tab[1].device != temb.device:
+        arr = (_lib.LinEntry * len(lins))()
+        col, offs = 0, []
+        for i, l in enumerate(lins):
+            arr[i] = _lib.LinEntry(l.weight.data_ptr(), l.bias.data_ptr() if l.bias is not None else None, l.out_features, col)
+            offs.append(col)
+            col += (l.out_features + 3) // 4 * 4            # 16-byte aligned slices -> float4 time-bias loads in the conv epilogue
+        dev_tab = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(temb.device)
+        tab = (sig, dev_tab, offs, col, max(l.out_features for l in lins))
+        object.__setattr__(model, "_ddpm_tp_table", tab)
+    _, dev_tab, offs, total, max_n = tab
+    B, K = temb.shape
+    out = E.f32(B, total)
+    _lib.call("ddpm_linear_grouped_fwd", temb.data_ptr(), B, K, temb.stride(0), dev_tab.data_ptr(), len(lins), max_n,
+              out.data_ptr(), total, 1, E.stream)
+    return [out[:, o:o + l.out_features] for o, l in zip(offs, lins)]
+
+
+def time_proj_bwd(E: Exec, temb: torch.Tensor, lin: torch.nn.Linear, dtb: torch.Tensor, dtemb: Optional[torch.Tensor]) -> torch.Tensor:
+    """dW, db of one time_proj and the accumulated d temb in one launch."""
+    B, K = temb.shape
+    accum = dtemb is not None
+    if dtemb is None:
+        dtemb = E.f32(B, K)
+    gw = grad_of(lin.weight)
+    if gw is None:
+        gw = torch.zeros_like(lin.weight)                   # frozen weight: gradient discarded
+    _lib.call("ddpm_time_proj_bwd", temb.data_ptr(), B, K, dtb.data_ptr(), dtb.stride(0), lin.out_features,
+              lin.weight.data_ptr(), gw.data_ptr(), _gptr(lin.bias), dtemb.data_ptr(), 1 if accum else 0, E.stream)
+    return dtemb
+
+
 # ----------------------------------------------------------------------------------------------
 # ResBlock  (unet_backbone.py:10-44)
 # ----------------------------------------------------------------------------------------------
@@ -709,7 +747,7 @@ def unet_forward(E: Exec, model, x: torch.Tensor, t: torch.Tensor, out_dtype: to
     # ---- time path: temb, then one fp32 [B][Cout] bias per ResBlock
     e0 = sinusoid(E, t, model.time_pos_emb.dim)
     temb, mlp_saved = time_mlp_fwd(E, model.time_mlp, e0)
-    tbs = [linear_fwd(E, temb, b.time_proj[1], True) for b in rbs]
+    tbs = time_proj_all_fwd(E, model, rbs, temb) if rbs else []
 
     # ---- concat buffers, one per decoder level: [cur | skip]
     enc_out_ch = []
@@ -832,7 +870,7 @@ def unet_backward(E: Exec, model, saved, dy: torch.Tensor, need_dx: bool, progre
         if kind == "res":
             _, blk, sv, i = ent
             dcur, dtb = resblock_bwd(E, blk, sv, dcur)
-            dtemb = linear_bwd(E, temb, blk.time_proj[1], True, dtb, dtemb, dtemb is not None)
+            dtemb = time_proj_bwd(E, temb, blk.time_proj[1], dtb, dtemb)
             if progress is not None:
                 progress(blk)
         elif kind == "attn":

@@ -166,6 +166,20 @@ int ddpm_set_tc_mode(int mode, int base_offset);
  * first-generation one-tile-per-CTA kernel (kept for A/B measurements) */
 int ddpm_set_tc_v2(int on);
 
+/* All time_proj linears of a UNet in one launch (unet_backbone.py:25-27,41): out[m][col0_i + n] =
+ * sum_k f(x[m][k]) W_i[n][k] + b_i[n], f = SiLU when a_silu.  `entries_dev` is an array in DEVICE memory. */
+typedef struct {
+    const float* w;      /* fp32 [N][K] (the nn.Linear weight itself) */
+    const float* bias;   /* fp32 [N] or NULL */
+    int32_t N, col0;     /* output features; first output column in `out` */
+} ddpm_lin_entry;
+int ddpm_linear_grouped_fwd(const float* x, int M, int K, int xpitch, const ddpm_lin_entry* entries_dev, int n,
+                            int max_N, float* out, int out_pitch, int a_silu, void* stream);
+/* Backward of one time_proj in one launch: dw[N][K] += dy^T silu(temb), db[N] += colsum(dy) (db may be NULL),
+ * dtemb[B][K] (+)= (dy W) * silu'(temb).  dy is [B][N] with row pitch dy_pitch. */
+int ddpm_time_proj_bwd(const float* temb, int B, int K, const float* dy, int dy_pitch, int N, const float* w,
+                       float* dw, float* db, float* dtemb, int accum_dtemb, void* stream);
+
 typedef struct {
     ddpm_tensor act;   /* forward input operand of the conv */
     ddpm_tensor dy;    /* gradient of the conv output */
