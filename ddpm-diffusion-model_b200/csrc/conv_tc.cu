@@ -1068,11 +1068,13 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restr
         for (int s = 0; s < splits; ++s) acc += ws[off + s * stride];
         dw[((size_t)co * p.CinV + ci) * taps + tap] += acc;
     }
-    if (p.ws_bias && p.dbias) {
-        for (int co = blockIdx.x * blockDim.x + threadIdx.x; co < p.CoutV; co += gridDim.x * blockDim.x) {
+    if (p.ws_bias && p.dbias) {                              // one warp per output channel, lanes stride over the partials
+        const int lane = threadIdx.x & 31, nwarp = (gridDim.x * blockDim.x) >> 5;
+        for (int co = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; co < p.CoutV; co += nwarp) {
             float acc = 0.f;
-            for (int s = 0; s < splits * grps; ++s) acc += p.ws_bias[((size_t)s * p.m_tiles + (co >> 7)) * 128 + (co & 127)];
-            p.dbias[co] += acc;
+            for (int s = lane; s < splits * grps; s += 32) acc += p.ws_bias[((size_t)s * p.m_tiles + (co >> 7)) * 128 + (co & 127)];
+            acc = warp_sum(acc);
+            if (lane == 0) p.dbias[co] += acc;
         }
     }
 }
