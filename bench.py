@@ -299,11 +299,11 @@ def run_ours(args):
         fl, tt, detail = conv_roofline(dev, B, shapes=C256_SHAPES if c256 else None)
         ach = fl / tt / 1e12
         # traffic: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel at the 96->96@64 shape
-        # (B=128), from the committed `ncu --set full` capture profiles/r1_ncu_prof_conv_tc2_96_64.txt
-        # (107.4 MB read = the input tensor once, 54.4 MB written back before the kernel ended; the algorithmic
+        # (B=128), from the committed `ncu --set full` capture profiles/r1_ncu_prof_final_conv_96_96_64.txt
+        # (107.3 MB read = the input tensor once, 61.6 MB written back before the kernel ended; the algorithmic
         # bytes of that launch are 107 MB in + 107 MB out + 0.17 MB weights)
         roof = {"bound": "tensor", "achieved": ach, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": ach / pk["tf_burst"],
-                "traffic": 161715200 if (B == 128 and not c256) else None, "traffic_shape": "96->96@64, B=128",
+                "traffic": 168904960 if (B == 128 and not c256) else None, "traffic_shape": "96->96@64, B=128",
                 "kernel": "conv_tc2_kernel (tcgen05 cta_group::2 implicit GEMM; 3x3 s1 layers of the %s UNet, count-weighted, B=%d)" % ("CelebA256" if c256 else "low-GPU", B),
                 "peak_source": pk["src"] + " bf16 burst (kernel timed alone)", "per_shape": detail,
                 "step_tensor_frac": (gf_train * 1e9 * world * B * args.steps / sec) / (world * pk["tf_sus"] * 1e12)}

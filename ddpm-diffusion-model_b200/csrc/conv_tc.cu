@@ -449,7 +449,7 @@ int conv_tc_launch(const ddpm_conv_args* a, cudaStream_t st) {
 // ================================================================================================
 // v2: persistent CTA-PAIR kernel (cta_group::2), TMEM double-buffered
 //
-// Why (ncu, profiles/r1_conv_tc_v1_192x192_64.txt): v1 re-fetches the whole 9-tap weight slab for every
+// Why (ncu, profiles/r1_ncu_prof_conv_tc_192_64.txt): v1 re-fetches the whole 9-tap weight slab for every
 // 128/256-pixel tile -- 87 % of its 3.3 GB of L2->SM traffic at 192->192@64 -- and two co-resident CTAs
 // fall into lock-step, so the tensor pipe is active 33 % of the time.  Here
 //   * two CTAs of a cluster (one TPC) issue M=256 MMAs: each CTA stages its own 128*MT pixel rows (A) but
