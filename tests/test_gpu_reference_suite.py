@@ -1,0 +1,233 @@
+"""The reference's own sanity suite (testing/*.py) re-run against the drop-in on a B200:
+shape / finiteness / determinism / gradient-flow assertions of test_attention.py, test_unet_backbone.py,
+test_ddim.py, test_difussion.py and test_training_components.py, plus the train-loop options the reference
+exposes (gradient accumulation, a non-Adam optimiser, fp32 without a scaler).  Everything runs through the
+C ABI; numerical parity with the reference itself is covered by test_gpu_parity.py."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def dev():
+    return torch.device("cuda", 0)
+
+
+def _mods():
+    from ddpm_diffusion_model_b200.model.attention import AttnBlock, SinusoidalPosEmb, TimeMLP
+    from ddpm_diffusion_model_b200.model.difussion_class import Diffusion
+    from ddpm_diffusion_model_b200.model.unet_backbone import ResBlock, UNetDenoiser, build_unet_64x64
+    return AttnBlock, SinusoidalPosEmb, TimeMLP, Diffusion, ResBlock, UNetDenoiser, build_unet_64x64
+
+
+# ---------------------------------------------------------------- testing/test_attention.py
+@pytest.mark.parametrize("cfg", [(8, 64, 4, 16), (16, 128, 4, 32), (32, 256, 8, 32)])
+def test_attn_block_shapes_and_determinism(cfg):
+    AttnBlock = _mods()[0]
+    hw, C, heads, d = cfg
+    torch.manual_seed(0)
+    blk = AttnBlock(C, num_heads=heads, head_dim=d).to(dev()).eval()
+    x = torch.randn(2, C, hw, hw, device=dev())
+    with torch.no_grad():
+        y1, y2 = blk(x), blk(x)
+    assert y1.shape == x.shape and torch.isfinite(y1).all()
+    assert torch.allclose(y1, y2, atol=1e-6)                       # test_attention.py:171
+
+
+@pytest.mark.parametrize("heads", [1, 2, 4, 8])
+def test_attn_block_heads(heads):
+    AttnBlock = _mods()[0]
+    torch.manual_seed(1)
+    blk = AttnBlock(64, num_heads=heads, head_dim=16).to(dev())
+    x = torch.randn(2, 64, 8, 8, device=dev(), requires_grad=True)
+    y = blk(x)
+    y.square().mean().backward()
+    assert y.shape == x.shape and torch.isfinite(x.grad).all()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in blk.parameters())
+
+
+def test_sinusoid_and_time_mlp():
+    _, SinusoidalPosEmb, TimeMLP, *_ = _mods()
+    t = torch.randint(0, 1000, (5,), device=dev())
+    for dim in (64, 513):                                          # odd dim is zero padded (attention.py:20-21)
+        e = SinusoidalPosEmb(dim)(t)
+        assert e.shape == (5, dim) and torch.isfinite(e).all()
+    mlp = TimeMLP(64, 128).to(dev())
+    e = SinusoidalPosEmb(64)(t).requires_grad_(True)
+    out = mlp(e)
+    out.sum().backward()
+    assert out.shape == (5, 128) and e.grad is not None and all(p.grad is not None for p in mlp.parameters())
+
+
+# ---------------------------------------------------------------- testing/test_unet_backbone.py
+def test_resblock_64_to_128():
+    ResBlock = _mods()[4]
+    blk = ResBlock(64, 128, 256, dropout=0.0).to(dev())
+    x = torch.randn(2, 64, 32, 32, device=dev()); temb = torch.randn(2, 256, device=dev())
+    y = blk(x, temb)
+    assert y.shape == (2, 128, 32, 32) and torch.isfinite(y).all()
+
+
+@pytest.mark.parametrize("size", [32, 64, 128])
+@pytest.mark.parametrize("amp", [False, True])
+def test_unet_input_sizes_and_grad_flow(size, amp):
+    """test_unet_backbone.py:176-195: a 64-px-built model on 32/64/128-px inputs; every parameter gets a gradient."""
+    build = _mods()[6]
+    torch.manual_seed(0)
+    model = build(base_channels=32, channel_mults=(1, 2, 2), num_res_blocks=1, attn_resolutions={16},
+                  num_heads=2, head_dim=16, dropout=0.0).to(dev()).train()
+    x = torch.randn(2, 3, size, size, device=dev()); t = torch.randint(0, 1000, (2,), device=dev())
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+        y = model(x, t)
+    assert y.shape == x.shape and torch.isfinite(y.float()).all()
+    y.float().square().mean().backward()
+    missing = [k for k, p in model.named_parameters() if p.grad is None or not torch.isfinite(p.grad).all()]
+    assert not missing, missing
+    assert sum(float(p.grad.abs().sum()) > 0 for p in model.parameters()) > 0.9 * len(list(model.parameters()))
+
+
+def test_unet_attention_adds_parameters():
+    UNetDenoiser = _mods()[5]
+    kw = dict(in_channels=3, base_channels=32, channel_mults=(1, 2), num_res_blocks=1, time_embed_dim=64, dropout=0.0,
+              num_heads=2, head_dim=16, img_resolution=32)
+    n0 = sum(p.numel() for p in UNetDenoiser(attn_resolutions=set(), **kw).parameters())
+    n1 = sum(p.numel() for p in UNetDenoiser(attn_resolutions={16}, **kw).parameters())
+    assert n1 > n0                                                  # test_unet_backbone.py:146
+
+
+# ---------------------------------------------------------------- testing/test_ddim.py, test_difussion.py
+def _tiny(eval_mode=True):
+    UNetDenoiser, Diffusion = _mods()[5], _mods()[3]
+    torch.manual_seed(0)
+    m = UNetDenoiser(3, 32, (1, 2), 1, {8}, 64, 0.0, 2, 16, 16).to(dev())
+    return (m.eval() if eval_mode else m.train()), Diffusion(T=1000).to(dev())
+
+
+def test_ddim_step_determinism_and_stochasticity():
+    model, d = _tiny()
+    x = torch.randn(3, 3, 16, 16, device=dev())
+    t = torch.full((3,), 500, device=dev(), dtype=torch.long); tp = torch.full((3,), 450, device=dev(), dtype=torch.long)
+    with torch.no_grad():
+        a = d.p_sample_step_ddim(model, x, t.clone(), tp.clone(), eta=0.0)
+        b = d.p_sample_step_ddim(model, x, t.clone(), tp.clone(), eta=0.0)
+        c1 = d.p_sample_step_ddim(model, x, t.clone(), tp.clone(), eta=1.0)
+        c2 = d.p_sample_step_ddim(model, x, t.clone(), tp.clone(), eta=1.0)
+    assert a.shape == x.shape and torch.isfinite(a).all()
+    assert torch.allclose(a, b, atol=1e-5)                          # test_ddim.py:72
+    assert not torch.allclose(c1, c2, atol=1e-5)                    # test_ddim.py:102
+
+
+@pytest.mark.parametrize("schedule", ["linear", "cosine"])
+def test_ddim_edges_and_chain(schedule):
+    UNetDenoiser, Diffusion = _mods()[5], _mods()[3]
+    torch.manual_seed(0)
+    model = UNetDenoiser(3, 32, (1, 2), 1, set(), 64, 0.0, 2, 16, 16).to(dev()).eval()
+    d = Diffusion(T=1000, schedule=schedule).to(dev())
+    x = torch.randn(2, 3, 16, 16, device=dev())
+    with torch.no_grad():
+        for cur, prev in ((999, 900), (1, 0), (0, 0)):              # edge timesteps (test_ddim.py:111-140)
+            t = torch.full((2,), cur, device=dev(), dtype=torch.long); tp = torch.full((2,), prev, device=dev(), dtype=torch.long)
+            assert torch.isfinite(d.p_sample_step_ddim(model, x, t, tp, eta=0.0)).all()
+        ts = torch.linspace(999, 0, 11).round().long().tolist()
+        for cur, prev in zip(ts[:-1], ts[1:]):                      # 10-step chain
+            t = torch.full((2,), cur, device=dev(), dtype=torch.long); tp = torch.full((2,), prev, device=dev(), dtype=torch.long)
+            x = d.p_sample_step_ddim(model, x, t, tp, eta=0.0)
+    assert torch.isfinite(x).all() and float(x.abs().max()) < 50
+
+
+def test_diffusion_end_to_end_smoke():
+    """testing/test_difussion.py: forward, loss + backward + AdamW step under AMP, q_sample statistics, one DDPM step."""
+    model, d = _tiny(eval_mode=False)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3)
+    torch.manual_seed(7)
+    x0 = torch.empty(4, 3, 16, 16, device=dev()).uniform_(-1, 1)
+    t = d.sample_timesteps(4, device=dev())
+    assert int(t.min()) >= 1 and int(t.max()) <= 999               # t = 0 is never trained (difussion_class.py:78)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        loss = d.loss_simple(model, x0, t)
+    assert torch.isfinite(loss)
+    before = [p.detach().clone() for p in model.parameters()]
+    loss.backward(); opt.step()
+    assert any(not torch.equal(a, b) for a, b in zip(before, model.parameters()))
+    big = torch.full((4096,), 999, device=dev(), dtype=torch.long)
+    xt = d.q_sample(torch.zeros(4096, 3, 4, 4, device=dev()), big)
+    assert abs(float(xt.std()) - float(d.sqrt_one_minus_alphas_cumprod[999])) < 0.02
+    with torch.no_grad():
+        out = d.p_sample_step(model.eval(), x0, torch.full((4,), 10, device=dev(), dtype=torch.long))
+    assert out.shape == x0.shape and torch.isfinite(out).all()
+
+
+def test_extract_clamps_in_place_like_the_reference():
+    from ddpm_diffusion_model_b200.model.difussion_utils import extract
+    a = torch.arange(10, dtype=torch.float32, device=dev())
+    t = torch.tensor([-3, 4, 99], device=dev())
+    out = extract(a, t, (3, 1, 2, 2))
+    assert out.shape == (3, 1, 1, 1) and out.flatten().tolist() == [0.0, 4.0, 9.0]
+    assert t.tolist() == [0, 4, 9]
+
+
+# ---------------------------------------------------------------- testing/test_training_components.py
+def test_ema_lifecycle_on_cuda():
+    from ddpm_diffusion_model_b200.training_loops.ema import EMA
+    model, _ = _tiny(eval_mode=False)
+    ema = EMA(model, decay=0.9)
+    params = list(model.parameters())
+    assert len(ema.shadow) == len(params) and all(torch.equal(s, p) for s, p in zip(ema.shadow, params))
+    with torch.no_grad():
+        for p in params:
+            p.add_(1.0)
+    old = [s.clone() for s in ema.shadow]
+    ema.update(model)
+    for s, o, p in zip(ema.shadow, old, params):                    # shadow = 0.9 old + 0.1 new
+        assert torch.allclose(s, 0.9 * o + 0.1 * p, atol=1e-5)
+    sd = ema.state_dict()
+    assert set(sd) == {"decay", "shadow"} and sd["shadow"] is ema.shadow      # live list (ema.py:33-35)
+    other = EMA(model, decay=0.5)
+    other.load_state_dict({"decay": 0.9, "shadow": [s.clone() for s in ema.shadow]})
+    assert other.decay == 0.9
+    other.copy_to(model)
+    for s, p in zip(ema.shadow, model.parameters()):
+        assert torch.allclose(s, p, atol=1e-5)                      # test_training_components.py:105
+
+
+def _loader(n_batches, B, seed=3):
+    g = torch.Generator().manual_seed(seed)
+    return [(torch.empty(B, 3, 16, 16).uniform_(-1, 1, generator=g), torch.zeros(B)) for _ in range(n_batches)]
+
+
+def test_train_one_epoch_grad_accum_and_return_values():
+    from ddpm_diffusion_model_b200.training_loops.ema import EMA
+    from ddpm_diffusion_model_b200.training_loops.grad_scaler import make_grad_scaler
+    from ddpm_diffusion_model_b200.training_loops.train_one_epoch import train_one_epoch
+    model, d = _tiny(eval_mode=False)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3)
+    ema = EMA(model, decay=0.99)
+    w0 = next(model.parameters()).detach().clone()
+    avg, nb, ni, gs = train_one_epoch(model, d, _loader(4, 4), opt, scaler=make_grad_scaler("cuda", True), ema=ema,
+                                      device="cuda:0", grad_accum_steps=2, base_lr=1e-3, warmup_steps=10, global_step=0)
+    assert (nb, ni, gs) == (4, 16, 2) and 0 < avg < 10              # 4 micro-batches -> 2 optimiser steps
+    assert abs(opt.param_groups[0]["lr"] - 1e-3 * 2 / 10) < 1e-12   # warm-up overwrites lr (train_one_epoch.py:86-89)
+    assert not torch.equal(w0, next(model.parameters()).detach())
+    avg2, nb2, _, gs2 = train_one_epoch(model, d, _loader(5, 4), opt, scaler=None, ema=ema, device="cuda:0", max_batches=3,
+                                        use_autocast=False, global_step=gs)
+    assert nb2 == 3 and gs2 == gs + 3 and avg2 == avg2
+
+
+def test_train_one_epoch_with_sgd_uses_the_generic_path():
+    """Any torch optimiser is accepted: non-Adam optimisers go through unscale+clip kernel + torch step."""
+    from ddpm_diffusion_model_b200.training_loops.train_one_epoch import train_one_epoch
+    model, d = _tiny(eval_mode=False)
+    opt = torch.optim.SGD(model.parameters(), lr=1e-2, momentum=0.9)
+    w0 = [p.detach().clone() for p in model.parameters()]
+    avg, nb, ni, gs = train_one_epoch(model, d, _loader(2, 4), opt, scaler=None, ema=None, device="cuda:0", use_autocast=False)
+    assert nb == 2 and gs == 2 and avg == avg
+    # (biases feeding a one-channel-per-group GroupNorm have an identically zero gradient, so not every tensor moves)
+    assert sum(not torch.equal(a, b.detach()) for a, b in zip(w0, model.parameters())) > 0.8 * len(w0)
+
+
+def test_cpu_inputs_fail_loudly():
+    model, d = _tiny()
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        d.q_sample(torch.zeros(1, 3, 4, 4), torch.zeros(1, dtype=torch.long))
+    with pytest.raises(RuntimeError, match="CUDA-only|no CPU fallback"):
+        model.cpu()(torch.zeros(1, 3, 16, 16), torch.zeros(1, dtype=torch.long))
