@@ -14,6 +14,15 @@
 namespace cg = cooperative_groups;
 
 #define NT 256
+#ifndef GN_FWD_OCC
+#define GN_FWD_OCC 4              // 64 registers, no spills: 83 vs 91 us at 96@64 (B=128) against 3 CTAs/SM
+#endif
+#ifndef GN_BWD_U
+#define GN_BWD_U 1                // with GN_BWD_OCC 4: 64 registers; +4..11 % over U = 2 at 3 CTAs/SM (occupancy beats ILP here)
+#endif
+#ifndef GN_BWD_OCC
+#define GN_BWD_OCC 4
+#endif
 
 struct PixMap {
     int cvs;    // channel vectors per pixel
@@ -146,7 +155,7 @@ __device__ __forceinline__ void cta_channel_reduce(float (*part)[NT], const floa
 
 // MODE 0: fused stats + apply; 1: stats only; 2: apply only (stats given)
 template <typename T, int VEC, int MODE>
-__global__ void __launch_bounds__(NT, 3) gn_fwd_kernel(GnP a) {
+__global__ void __launch_bounds__(NT, GN_FWD_OCC) gn_fwd_kernel(GnP a) {
     extern __shared__ __align__(16) unsigned char gsm[];
     const int C = a.x.C, G = a.G, cpg = C / G, HW = a.x.H * a.x.W, W = a.x.W;
     double* chan = reinterpret_cast<double*>(gsm);           // [2][C]
@@ -261,7 +270,7 @@ __global__ void __launch_bounds__(NT, 3) gn_fwd_kernel(GnP a) {
 //   S1[c] = sum_p dz, S2[c] = sum_p dz*xhat;  A_g = mean_g(gamma*S1), B_g = mean_g(gamma*S2)
 //   dx = rstd * (dz*gamma - A_g - xhat*B_g);  dbeta += S1, dgamma += S2
 template <typename T, int VEC, bool STASH>
-__global__ void __launch_bounds__(NT, STASH ? 3 : 2) gn_bwd_kernel(GnP a) {
+__global__ void __launch_bounds__(NT, STASH ? GN_BWD_OCC : 2) gn_bwd_kernel(GnP a) {
     extern __shared__ __align__(16) unsigned char gsm[];
     const int C = a.x.C, G = a.G, cpg = C / G, HW = a.x.H * a.x.W;
     double* chan = reinterpret_cast<double*>(gsm);           // [2][C] this CTA's per-channel partials (read by peers)
@@ -284,7 +293,7 @@ __global__ void __launch_bounds__(NT, STASH ? 3 : 2) gn_bwd_kernel(GnP a) {
     const T* xb = img_origin<T>(a.x, n, c0);
     T* db = img_origin<T>(a.dy, n, c0);
     T* ob = img_origin<T>(a.o, n, c0);
-    constexpr int U = 2;
+    constexpr int U = GN_BWD_U;
 
     for (int g = threadIdx.x; g < G; g += NT) {
         const double s = a.stats[((size_t)n * G + g) * 2], q = a.stats[((size_t)n * G + g) * 2 + 1];
