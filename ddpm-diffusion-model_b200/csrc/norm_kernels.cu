@@ -17,6 +17,9 @@ namespace cg = cooperative_groups;
 #ifndef GN_FWD_OCC
 #define GN_FWD_OCC 4              // 64 registers, no spills: 83 vs 91 us at 96@64 (B=128) against 3 CTAs/SM
 #endif
+#ifndef GN_FWD_U
+#define GN_FWD_U 4
+#endif
 #ifndef GN_BWD_U
 #define GN_BWD_U 1                // with GN_BWD_OCC 4: 64 registers; +4..11 % over U = 2 at 3 CTAs/SM (occupancy beats ILP here)
 #endif
@@ -175,7 +178,7 @@ __global__ void __launch_bounds__(NT, GN_FWD_OCC) gn_fwd_kernel(GnP a) {
     const PixAddr ax(a.x, a.wshift), ao(a.o, a.wshift);
     const T* xb = img_origin<T>(a.x, n, c0);
     T* ob = img_origin<T>(a.o, n, c0);
-    constexpr int U = 4;
+    constexpr int U = GN_FWD_U;
 
     if (MODE != 2) {
         float acc[2 * VEC];
