@@ -20,6 +20,7 @@
 // for fprop and, with flipped/transposed weights, dgrad.
 #include "common.cuh"
 #include <cuda.h>
+#include <cooperative_groups.h>
 #include <type_traits>
 #include <cudaTypedefs.h>
 
@@ -917,8 +918,12 @@ struct WgTcParams {
     // D_bias[co][*] = sum_Q dY[Q][co] (halo rows of dY are zero), instead of a separate pass over dY
     float* ws_bias;             // [split][mtile][128] partials (NULL: no bias gradient)
     float* dbias;               // fp32 [CoutV], accumulated by the reduce kernel
+    float* dw;                  // fp32 OIHW gradient; non-NULL: cooperative launch, the split-K partials are reduced
+                                // by the same kernel behind a grid barrier (no second launch)
 };
 
+__device__ __forceinline__ void wgrad_reduce_body(const float* __restrict__ ws, float* __restrict__ dw, int splits, const WgTcParams& p,
+                                                  int gtid, int gthreads);
 __global__ void __launch_bounds__(TC_THREADS) wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY,
                                                                const __grid_constant__ CUtensorMap tmA, WgTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -1050,14 +1055,22 @@ __global__ void __launch_bounds__(TC_THREADS) wgrad_tc_kernel(const __grid_const
     }
     __syncthreads();
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
+    if (p.dw) {
+        // split-K reduction in the same (cooperative) launch: every CTA's partial tile is in the workspace after the
+        // grid barrier; all threads of the grid then sum disjoint slices of the gradient
+        cooperative_groups::this_grid().sync();
+        const int bid = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        wgrad_reduce_body(p.ws, p.dw, gridDim.x, p, bid * TC_THREADS + threadIdx.x, gridDim.x * gridDim.y * gridDim.z * TC_THREADS);
+    }
 }
 
 // dw[co][ci][ky][kx] += sum_split ws[split][mtile][ky*n_tiles+ntile][co%128][kx*NT + ci%NT]
-__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int splits, WgTcParams p) {
+__device__ __forceinline__ void wgrad_reduce_body(const float* __restrict__ ws, float* __restrict__ dw, int splits, const WgTcParams& p,
+                                                  int gtid, int gthreads) {
     const int taps = p.ntap * p.ntap;
     const int total = p.CoutV * taps * p.CinV;
     const int grps = p.ntap * p.n_tiles, cols = p.ntap * p.NT;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    for (int i = gtid; i < total; i += gthreads) {
         // enumerate (co, tap, ci) with ci fastest so workspace reads are coalesced
         int ci = i % p.CinV; int r = i / p.CinV; int tap = r % taps; int co = r / taps;
         int ky = tap / p.ntap, kx = tap - ky * p.ntap;
@@ -1069,14 +1082,17 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restr
         dw[((size_t)co * p.CinV + ci) * taps + tap] += acc;
     }
     if (p.ws_bias && p.dbias) {                              // one warp per output channel, lanes stride over the partials
-        const int lane = threadIdx.x & 31, nwarp = (gridDim.x * blockDim.x) >> 5;
-        for (int co = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; co < p.CoutV; co += nwarp) {
+        const int lane = gtid & 31, nwarp = gthreads >> 5;
+        for (int co = gtid >> 5; co < p.CoutV; co += nwarp) {
             float acc = 0.f;
             for (int s = lane; s < splits * grps; s += 32) acc += p.ws_bias[((size_t)s * p.m_tiles + (co >> 7)) * 128 + (co & 127)];
             acc = warp_sum(acc);
             if (lane == 0) p.dbias[co] += acc;
         }
     }
+}
+__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int splits, WgTcParams p) {
+    wgrad_reduce_body(ws, dw, splits, p, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
 
 static int sm_count() {
@@ -1159,6 +1175,20 @@ int wgrad_tc_launch(const ddpm_wgrad_args* a, cudaStream_t st) {
         configured = smem;
     }
     dim3 grid(splits, p.ntap * p.n_tiles, p.m_tiles);
+    // In-kernel split-K reduction behind a cooperative grid barrier: measured SLOWER on B200 (a cooperative launch costs
+    // ~50 us: 96->96@64 100 -> 153 us), so it stays an experiment (bit 8 of the flags); default = separate reduce kernel.
+    const bool fused = (g_tc_exp & 256) && (int)(grid.x * grid.y * grid.z) <= sm_count();
+    p.dw = fused ? a->dw : nullptr;
+    if (fused) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, wgrad_tc_kernel, tmY, tmA, p));
+        LAUNCH_OK();
+        return 0;
+    }
     wgrad_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmY, tmA, p);
     LAUNCH_OK();
     int total = p.CoutV * p.ntap * p.ntap * p.CinV;
