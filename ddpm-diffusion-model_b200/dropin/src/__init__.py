@@ -22,6 +22,8 @@ _MAP = {
     "src.training_loops.grad_scaler": f"{_PKG}.training_loops.grad_scaler",
     "src.training_loops.training_utils": f"{_PKG}.training_loops.training_utils",
     "src.training_loops.train_one_epoch": f"{_PKG}.training_loops.train_one_epoch",
+    "src.training_loops.main_train_loop": f"{_PKG}.training_loops.main_train_loop",
+    "src.training_loops.chekpoints": f"{_PKG}.training_loops.chekpoints",
     "src.testing": f"{_PKG}.testing",
     "src.testing.ddpm_inference": f"{_PKG}.testing.ddpm_inference",
     "src.testing.ddpim_inference": f"{_PKG}.testing.ddpim_inference",

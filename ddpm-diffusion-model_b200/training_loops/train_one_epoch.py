@@ -60,7 +60,13 @@ class FusedStep:
                 opt.state[p] = {"step": self.step[0], "exp_avg": a, "exp_avg_sq": b}
 
     def still_valid(self, model, optimizer, arena) -> bool:
-        return model is self.model and optimizer is self.opt and arena is self.arena and arena.valid()
+        if not (model is self.model and optimizer is self.opt and arena is self.arena and arena.valid()):
+            return False
+        if self.fusable:                                  # optimizer.load_state_dict() replaces the state tensors
+            st = optimizer.state.get(arena.params[-1])
+            if not st or st["exp_avg"].data_ptr() != self.m.data_ptr() + 4 * arena.offsets[-1]:
+                return False
+        return True
 
     def run(self, scaler, use_scaler: bool, grad_clip, ema):
         ar = self.arena

@@ -231,3 +231,68 @@ def test_cpu_inputs_fail_loudly():
         d.q_sample(torch.zeros(1, 3, 4, 4), torch.zeros(1, dtype=torch.long))
     with pytest.raises(RuntimeError, match="CUDA-only|no CPU fallback"):
         model.cpu()(torch.zeros(1, 3, 16, 16), torch.zeros(1, dtype=torch.long))
+
+
+# ---------------------------------------------------------------- main_train_loop.py / chekpoints.py
+def test_train_ddpm_checkpoint_resume_and_reference_format(tmp_path, capsys):
+    from ddpm_diffusion_model_b200.training_loops.chekpoints import load_ckpt, save_ckpt
+    from ddpm_diffusion_model_b200.training_loops.ema import EMA
+    from ddpm_diffusion_model_b200.training_loops.main_train_loop import train_ddpm
+    from ddpm_diffusion_model_b200.training_loops.training_utils import sample_ddpm
+    model, d = _tiny(eval_mode=False)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3)
+    ema = EMA(model, decay=0.9)
+    d_small = _mods()[3](T=20).to(dev())                                  # 20-step sampler keeps the test short
+    train_ddpm(model, d_small, _loader(3, 4), opt, ema, device="cuda:0", epochs=2, base_lr=1e-3, warmup_steps=4,
+               sample_every=1, sample_n=4, img_size=16, sample_fn=sample_ddpm, ckpt_dir=str(tmp_path), run_name="t",
+               save_every=1, ckpt_utils=(save_ckpt, load_ckpt))
+    out = capsys.readouterr().out
+    assert "DDPM run: t" in out and "[SAMPLE]" in out and "[CKPT]" in out
+    for f in ("t_e000.pt", "t_e001.pt", "t_last.pt", "t_samples_e001.png"):
+        assert (tmp_path / f).exists(), f
+    ck = torch.load(tmp_path / "t_last.pt", map_location="cpu", weights_only=False)
+    assert set(ck) == {"model", "optimizer", "scaler", "ema", "step", "extra"} and ck["step"] == 6      # chekpoints.py:5-12
+    assert list(ck["model"]) == list(model.state_dict()) and len(ck["ema"]["shadow"]) == len(list(model.parameters()))
+    assert ck["optimizer"]["state"][0]["exp_avg"].shape == next(model.parameters()).shape
+    # resume into a fresh model/optimizer: weights, Adam moments and EMA come back; training continues at epoch 2
+    model2, _ = _tiny(eval_mode=False)
+    with torch.no_grad():
+        for p in model2.parameters():
+            p.add_(0.5)
+    opt2 = torch.optim.AdamW(model2.parameters(), lr=1e-3)
+    ema2 = EMA(model2, decay=0.5)
+    train_ddpm(model2, d_small, _loader(3, 4, seed=9), opt2, ema2, device="cuda:0", epochs=3, base_lr=1e-3, warmup_steps=4,
+               sample_fn=None, ckpt_dir=str(tmp_path), run_name="r", ckpt_utils=(save_ckpt, load_ckpt),
+               resume_path=str(tmp_path / "t_last.pt"), override_lr=5e-4)
+    out = capsys.readouterr().out
+    assert "[RESUME] Cargado" in out and "start_epoch=2" in out and "override_lr" in out
+    assert ema2.decay == 0.9
+    ck2 = torch.load(tmp_path / "r_last.pt", map_location="cpu", weights_only=False)
+    assert ck2["step"] == 9 and ck2["extra"] == {"epoch": 2, "global_step": 9}
+    # one epoch of 3 steps from the restored state: parameters moved away from the checkpoint, but not by the +0.5 offset
+    w_ck, w_new = ck["model"]["in_conv.weight"], ck2["model"]["in_conv.weight"]
+    assert 0 < float((w_new - w_ck).abs().max()) < 0.1
+
+
+def test_checkpoint_round_trip_restores_fused_state(tmp_path):
+    from ddpm_diffusion_model_b200.training_loops.chekpoints import load_ckpt, save_ckpt
+    from ddpm_diffusion_model_b200.training_loops.ema import EMA
+    from ddpm_diffusion_model_b200.training_loops.grad_scaler import make_grad_scaler
+    from ddpm_diffusion_model_b200.training_loops.train_one_epoch import train_one_epoch
+    model, d = _tiny(eval_mode=False)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3)
+    ema, scaler = EMA(model, decay=0.9), make_grad_scaler("cuda", True)
+    data = _loader(4, 4)
+    _, _, _, gs = train_one_epoch(model, d, data[:2], opt, scaler=scaler, ema=ema, device="cuda:0")
+    save_ckpt(str(tmp_path / "a.pt"), model, opt, scaler, ema, step=gs)
+    torch.manual_seed(11)
+    ref = train_one_epoch(model, d, data[2:], opt, scaler=scaler, ema=ema, device="cuda:0", global_step=gs)
+    w_ref = [p.detach().clone() for p in model.parameters()]
+    # restore and repeat the same two steps with the same RNG: identical result (moments and EMA restored)
+    step, extra = load_ckpt(str(tmp_path / "a.pt"), model, opt, scaler, ema, map_location="cuda:0")
+    assert step == gs and extra == {}
+    torch.manual_seed(11)
+    again = train_one_epoch(model, d, data[2:], opt, scaler=scaler, ema=ema, device="cuda:0", global_step=gs)
+    assert abs(again[0] - ref[0]) < 1e-4 * abs(ref[0])
+    for a, b in zip(w_ref, model.parameters()):
+        assert torch.allclose(a, b.detach(), rtol=1e-4, atol=1e-6)

@@ -224,3 +224,57 @@ def test_gradient_buckets_gloo_world2():
     for p in procs:
         p.join(30)
     assert res == [(0, True), (1, True)]
+
+
+def test_checkpoint_format_is_the_reference_format(tmp_path):
+    """chekpoints.py:4-25: same dictionary; a file written here loads with plain torch.load (weights_only) and, when the
+    reference checkout is present (authoring container only), with the reference's own load_ckpt into its own classes."""
+    from ddpm_diffusion_model_b200.model.unet_backbone import UNetDenoiser
+    from ddpm_diffusion_model_b200.training_loops.chekpoints import load_ckpt, save_ckpt
+    from ddpm_diffusion_model_b200.training_loops.ema import EMA
+    kw = dict(in_channels=3, base_channels=32, channel_mults=(1, 2), num_res_blocks=1, attn_resolutions={8}, time_embed_dim=64,
+              dropout=0.0, num_heads=2, head_dim=16, img_resolution=16)
+    torch.manual_seed(0)
+    model = UNetDenoiser(**kw)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3)
+    for p in model.parameters():                       # give the optimiser a state without running a kernel
+        p.grad = torch.full_like(p, 1e-3)
+    opt.step()
+    ema = EMA(model, decay=0.99)
+    scaler = torch.amp.GradScaler("cuda", enabled=False)
+    path = str(tmp_path / "ck.pt")
+    save_ckpt(path, model, opt, scaler, ema, step=7, extra={"epoch": 1, "global_step": 7})
+    ck = torch.load(path, map_location="cpu", weights_only=True)
+    assert set(ck) == {"model", "optimizer", "scaler", "ema", "step", "extra"}
+    assert all(torch.equal(ck["model"][k], v) for k, v in model.state_dict().items())
+    # no tensor drags a shared storage along
+    assert ck["ema"]["shadow"][0].untyped_storage().nbytes() == ck["ema"]["shadow"][0].numel() * 4
+    m2 = UNetDenoiser(**kw)
+    o2 = torch.optim.AdamW(m2.parameters(), lr=1e-3)
+    e2 = EMA(m2, decay=0.5)
+    step, extra = load_ckpt(path, m2, o2, scaler, e2, map_location="cpu")
+    assert step == 7 and extra == {"epoch": 1, "global_step": 7} and e2.decay == 0.99
+    assert all(torch.equal(a, b) for a, b in zip(m2.state_dict().values(), model.state_dict().values()))
+    assert torch.equal(o2.state[next(m2.parameters())]["exp_avg"], opt.state[next(model.parameters())]["exp_avg"])
+    ref_root = "/root/reference"
+    if not os.path.isdir(os.path.join(ref_root, "src")):
+        return
+    import subprocess
+    code = f"""
+import sys, torch
+sys.path.insert(0, {ref_root!r})
+from src.model.unet_backbone import UNetDenoiser
+from src.training_loops.ema import EMA
+from src.training_loops.chekpoints import load_ckpt
+m = UNetDenoiser(**{kw!r})
+o = torch.optim.AdamW(m.parameters(), lr=1e-3)
+e = EMA(m, decay=0.5)
+s = torch.amp.GradScaler("cuda", enabled=False)
+step, extra = load_ckpt({path!r}, m, o, s, e, map_location="cpu")
+ck = torch.load({path!r}, map_location="cpu")
+assert step == 7 and e.decay == 0.99 and len(e.shadow) == len(list(m.parameters()))
+assert all(torch.equal(ck["model"][k], v) for k, v in m.state_dict().items())
+print("reference-load-ok")
+"""
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert "reference-load-ok" in r.stdout, r.stderr[-2000:]
