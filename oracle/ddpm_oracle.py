@@ -114,7 +114,7 @@ def predict_x0(tb, x_t: Tensor, eps: Tensor, t: Tensor, clamp_x0: bool = True,
     x0 = (x_t - so * eps) / (sa + 1e-12)
     if dynamic_threshold is not None:
         amax = x0.abs().flatten(1).max(dim=1).values
-        amax = torch.maximum(amax, torch.ones((), dtype=x0.dtype))
+        amax = torch.maximum(amax, torch.ones((), dtype=x0.dtype, device=x0.device))
         div = amax.clamp(min=dynamic_threshold).view(-1, *([1] * (x0.ndim - 1)))
         x0 = (x0 / div).clamp(-1, 1)
     elif clamp_x0:
@@ -184,7 +184,7 @@ class UNetSpec:
 def sinusoidal(t: Tensor, dim: int) -> Tensor:
     """attention.py:13-22 (note the ``half-1`` denominator and zero pad for odd dim)."""
     half = dim // 2
-    freq = torch.exp(torch.arange(half, dtype=torch.float32) * -(math.log(10000) / (half - 1)))
+    freq = torch.exp(torch.arange(half, dtype=torch.float32) * -(math.log(10000) / (half - 1))).to(t.device)
     ang = t.float()[:, None] * freq[None, :]
     out = torch.cat([ang.sin(), ang.cos()], dim=1)
     if dim % 2 == 1:
