@@ -9,9 +9,11 @@ Workload (BASELINE.json configs[1]): CelebA64 low-GPU UNetDenoiser (12.68 M para
 betas, bf16 autocast + GradScaler + AdamW(lr 2e-4) + EMA(0.9995) + grad-clip 1.0, batch 128 per GPU,
 synthetic 64x64 images, data-parallel over N GPUs (weak scaling).  One "step" = one optimiser step.
 
-  value    : images/s, whole job, batch already resident in HBM when the timed region starts
-  e2e      : same metric through the public API (`train_one_epoch`, one call per step) with the batch
-             in pinned HOST memory: H2D copy of the images and D2H read of the loss inside the timing
+  value    : images/s, whole job, batch already resident in HBM when the timed region starts; the K timed steps are
+             ONE `train_one_epoch` call over a K-batch loader (the reference API's unit of work)
+  e2e      : same metric through the public API with every batch in pinned HOST memory: per step the H2D copy of
+             the images and a D2H DMA of the step's loss (pinned trace) inside the timing; `sync_every_step` is the
+             same with one call per step (host reads the loss after every step)
   roofline : the dominant kernel (implicit-GEMM convolution) timed alone with CUDA events on the
              launching stream, algorithmic FLOPs / time vs the measured bf16 peak
   cpu_baseline / --impl reference : the oracle port of the reference (CPU, fp32, all host threads)
@@ -211,25 +213,34 @@ def run_ours(args):
     y_host = torch.zeros(B)
     x_dev = x_host.to(dev)
 
-    def step_resident():
-        return train_one_epoch(model, diff, [(x_dev, y_host)], opt, scaler=scaler, ema=ema, device=f"cuda:{local}", grad_clip=1.0)
+    # One `train_one_epoch` call over a K-batch loader is the reference API's unit of work (train_one_epoch.py:11);
+    # inside it nothing synchronises with the host until the epoch's mean loss is read, so the enqueue of step i+1
+    # overlaps the GPU work of step i.  (One call PER step drains the GPU at every call boundary: +2.5 ms/step of
+    # idle GPU, measured with tools/step_timeline.py; reported below as `sync_every_step`.)
+    def step_resident(K=1):
+        return train_one_epoch(model, diff, [(x_dev, y_host)] * K, opt, scaler=scaler, ema=ema, device=f"cuda:{local}", grad_clip=1.0)
 
-    def step_e2e():
-        return train_one_epoch(model, diff, [(x_host, y_host)], opt, scaler=scaler, ema=ema, device=f"cuda:{local}", grad_clip=1.0)
+    # e2e: every step copies its batch from pinned host memory (x.to(device, non_blocking=True) inside the loop,
+    # train_one_epoch.py:62) and DMAs its 4-byte loss back into a pinned trace (`last_step_losses()`).
+    def step_e2e(K=1):
+        return train_one_epoch(model, diff, [(x_host, y_host)] * K, opt, scaler=scaler, ema=ema, device=f"cuda:{local}", grad_clip=1.0)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed(fn, K):
+    def timed(fn, K, per_call=False):
         barrier()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         _lib.launch_count(reset=True)
         s.record()
         last = None
-        for _ in range(K):
-            last = fn()
+        if per_call:
+            for _ in range(K):
+                last = fn()
+        else:
+            last = fn(K)
         e.record()
         barrier()
         ms = s.elapsed_time(e)
@@ -249,16 +260,19 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
         torch.cuda.nvtx.range_pop()
         return
-    for _ in range(max(3, args.warmup)):
-        step_resident()
+    step_resident(max(3, args.warmup))
     from ddpm_diffusion_model_b200 import engine as _engine
     miss0 = _engine.POOL.misses
     with ClockSampler(local) as clk:
         sec, launches, last = timed(step_resident, args.steps)
     pool_misses = _engine.POOL.misses - miss0
-    for _ in range(2):
-        step_e2e()
+    step_e2e(2)
     sec_e2e, _, last_e2e = timed(step_e2e, args.steps)
+    from ddpm_diffusion_model_b200.training_loops.train_one_epoch import last_step_losses
+    trace = last_step_losses()
+    assert trace.numel() == args.steps and bool(torch.isfinite(trace).all()), "per-step loss trace incomplete"
+    sec_sync, _, _ = timed(step_e2e, min(args.steps, 20), per_call=True)
+    sec_sync /= min(args.steps, 20)
     value = world * B * args.steps / sec
     e2e = world * B * args.steps / sec_e2e
 
@@ -319,9 +333,14 @@ def run_ours(args):
             "config": {"workload": ("CelebA256 attention UNet (63.1M)" if c256 else "CelebA64 low-GPU UNet (12.68M)") +
                        " training step: bf16 autocast + GradScaler + AdamW + EMA + clip",
                        "batch_per_gpu": B, "global_batch": B * world, "img": IMG, "T": 1000, "parallelism": f"dp{world}",
+                       "timed": "one train_one_epoch call over K batches",
                        "l2": "working set per step (~3 GB of activations) exceeds the 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e, "unit": "img/s", "h2d_bytes_per_step": B * 3 * IMG * IMG * 4, "d2h_bytes_per_step": 4,
-                    "ms_per_step": sec_e2e / args.steps * 1e3},
+                    "ms_per_step": sec_e2e / args.steps * 1e3,
+                    "timed": "one train_one_epoch call over K pinned host batches: H2D of the batch and D2H of the step loss "
+                             "(pinned trace) every step, one synchronising read of the mean loss at the end",
+                    "sync_every_step": {"value": world * B / sec_sync, "ms_per_step": sec_sync * 1e3,
+                                        "timed": "one train_one_epoch call PER step (host reads the loss after every step)"}},
             "gpu_launches": launches, "clocks": clk.summary(), "roofline": roof, "cpu_baseline": cpu,
             "loss": last[0] if last else None, "pool_misses_in_timed_region": pool_misses, "ddim100": ddim,
             "train_tflops_per_gpu": gf_train * 1e9 * B * args.steps / sec / 1e12,

@@ -24,6 +24,39 @@ def _stream(dev) -> int:
     return torch.cuda.current_stream(dev).cuda_stream
 
 
+class _LossTrace:
+    """Per-step losses of the last epoch without a per-step host sync: every step DMAs its 4-byte loss into a pinned
+    host chunk (non-blocking); the values are valid once `train_one_epoch` has returned (it ends with one
+    synchronising read of the device-side sum).  `last_step_losses()` returns them as a CPU tensor."""
+    CHUNK = 1024
+
+    def __init__(self):
+        self.chunks, self.n = [], 0
+
+    def reset(self):
+        self.n = 0
+
+    def push(self, loss: torch.Tensor):
+        c, k = divmod(self.n, self.CHUNK)
+        if c == len(self.chunks):
+            self.chunks.append(torch.empty(self.CHUNK, dtype=torch.float32).pin_memory())
+        self.chunks[c][k].copy_(loss, non_blocking=True)
+        self.n += 1
+
+    def values(self) -> torch.Tensor:
+        if self.n == 0:
+            return torch.empty(0)
+        return torch.cat(self.chunks)[:self.n].clone()
+
+
+_TRACE = _LossTrace()
+
+
+def last_step_losses() -> torch.Tensor:
+    """Losses of every micro-batch of the most recent `train_one_epoch` call (fp32, CPU)."""
+    return _TRACE.values()
+
+
 class FusedStep:
     """Owns the flat Adam moments / step counter and runs the fused optimiser-side pass."""
 
@@ -149,6 +182,7 @@ def train_one_epoch(model, diffusion, dataloader, optimizer, *, scaler=None, ema
     use_scaler = bool(use_autocast and (scaler is not None))
 
     loss_sum = torch.zeros((), dtype=torch.float32, device=dev)
+    _TRACE.reset()
     n_seen_batches, n_seen_images = 0, 0
     did_header = False
     if log_every and global_step == 0:
@@ -200,7 +234,9 @@ def train_one_epoch(model, diffusion, dataloader, optimizer, *, scaler=None, ema
                     gnorm = fused.grad_norm(scaler, use_scaler)
                 global_step += 1
 
-            loss_sum += loss.detach().float() * grad_accum_steps
+            step_loss = loss.detach().float() * grad_accum_steps
+            loss_sum += step_loss
+            _TRACE.push(step_loss)
             n_seen_batches += 1
             n_seen_images += B
 
