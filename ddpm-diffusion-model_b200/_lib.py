@@ -106,6 +106,7 @@ SIGNATURES = {
     "ddpm_set_force_simt": [_i],
     "ddpm_set_tc_mode": [_i, _i],
     "ddpm_set_tc_v2": [_i],
+    "ddpm_set_pdl": [_i],
 }
 
 

@@ -576,6 +576,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_c
     cluster_sync_all();                                  // peer's barriers are initialised before anyone signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_enter();                                         // everything above overlapped the previous kernel's tail
 
     if (warp == 0) {
         // ===================================================================== TMA producer (both CTAs)
@@ -875,10 +876,11 @@ static int conv_tc2_launch(const ddpm_conv_args* a, cudaStream_t st) {
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(TC2_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2]; unsigned nat = 1;
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    pdl_attr(at, &nat);
+    cfg.attrs = at; cfg.numAttrs = nat;
     static size_t configured[4] = {0, 0, 0, 0};
 #define TC2_GO(MTV, TAPSV, SLOT) { \
         if (smem > configured[SLOT]) { CUDA_TRY(cudaFuncSetAttribute(conv_tc2_kernel<MTV, TAPSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured[SLOT] = smem; } \
@@ -961,6 +963,7 @@ __global__ void __launch_bounds__(TC_THREADS) wgrad_tc_kernel(const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t bias_col = (uint32_t)(p.ntap * p.NT);
+    pdl_enter();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -1092,6 +1095,7 @@ __device__ __forceinline__ void wgrad_reduce_body(const float* __restrict__ ws, 
     }
 }
 __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int splits, WgTcParams p) {
+    pdl_enter();
     wgrad_reduce_body(ws, dw, splits, p, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
 
@@ -1189,11 +1193,11 @@ int wgrad_tc_launch(const ddpm_wgrad_args* a, cudaStream_t st) {
         LAUNCH_OK();
         return 0;
     }
-    wgrad_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmY, tmA, p);
+    CUDA_TRY(launch_pdl(wgrad_tc_kernel, grid, dim3(TC_THREADS), smem, st, tmY, tmA, p));
     LAUNCH_OK();
     int total = p.CoutV * p.ntap * p.ntap * p.CinV;
     int rg = (total + 255) / 256; if (rg > 148 * 8) rg = 148 * 8;
-    wgrad_reduce_kernel<<<rg, 256, 0, st>>>(p.ws, a->dw, splits, p);
+    CUDA_TRY(launch_pdl(wgrad_reduce_kernel, dim3(rg), dim3(256), 0, st, (const float*)p.ws, a->dw, splits, p));
     LAUNCH_OK();
     return 0;
 }

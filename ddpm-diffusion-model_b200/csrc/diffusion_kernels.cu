@@ -6,10 +6,14 @@
 //
 // HBM roofline (fp32 tensors): q_sample 12 B/elem, MSE 8 (6 with bf16 pred), DDPM step 16,
 // DDIM step 12 (eta=0) / 16, to_image01 8.
+#include <stdlib.h>
 #include "common.cuh"
 #include <math.h>
 
 int64_t g_ddpm_launches = 0;
+static int pdl_default() { const char* e = getenv("DDPM_B200_PDL"); return !(e && e[0] == '0'); }
+int g_ddpm_pdl = pdl_default();
+extern "C" int ddpm_set_pdl(int on) { g_ddpm_pdl = on ? 1 : 0; return 0; }
 
 #define TMAX 1024
 #define NTAB 10

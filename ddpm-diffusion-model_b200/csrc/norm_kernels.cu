@@ -160,6 +160,7 @@ __device__ __forceinline__ void cta_channel_reduce(float (*part)[NT], const floa
 template <typename T, int VEC, int MODE>
 __global__ void __launch_bounds__(NT, GN_FWD_OCC) gn_fwd_kernel(GnP a) {
     extern __shared__ __align__(16) unsigned char gsm[];
+    pdl_enter();
     const int C = a.x.C, G = a.G, cpg = C / G, HW = a.x.H * a.x.W, W = a.x.W;
     double* chan = reinterpret_cast<double*>(gsm);           // [2][C]
     double* gpart = chan + 2 * C;                            // [2][G]  (read by the other CTAs of the cluster)
@@ -275,6 +276,7 @@ __global__ void __launch_bounds__(NT, GN_FWD_OCC) gn_fwd_kernel(GnP a) {
 template <typename T, int VEC, bool STASH>
 __global__ void __launch_bounds__(NT, STASH ? GN_BWD_OCC : 2) gn_bwd_kernel(GnP a) {
     extern __shared__ __align__(16) unsigned char gsm[];
+    pdl_enter();
     const int C = a.x.C, G = a.G, cpg = C / G, HW = a.x.H * a.x.W;
     double* chan = reinterpret_cast<double*>(gsm);           // [2][C] this CTA's per-channel partials (read by peers)
     float* tot = reinterpret_cast<float*>(chan + 2 * C);     // [2][C] cluster totals
@@ -449,10 +451,11 @@ template <typename K>
 static int launch_cluster(K kernel, int grid, int cs, size_t smem, cudaStream_t st, GnP& p) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2]; unsigned nat = 1;
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    pdl_attr(at, &nat);
+    cfg.attrs = at; cfg.numAttrs = nat;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, p);
     if (e != cudaSuccess) return (int)e;
     LAUNCH_OK();
@@ -558,6 +561,7 @@ extern "C" int ddpm_gn_bwd_colsum(const ddpm_tensor* x, int dtype, int groups, c
 // generic walker over (n, y, x, cv) of the OUTPUT view
 template <typename T, int VEC, typename F>
 __global__ void __launch_bounds__(NT) pix_kernel(int N, int H, int W, int C, F f) {
+    pdl_enter();
     const int cvs = C / VEC;
     const int64_t total = (int64_t)N * H * W * cvs;
     for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < total; i += (int64_t)gridDim.x * NT) {
@@ -584,7 +588,7 @@ extern "C" int ddpm_upsample2x(const ddpm_tensor* x, const ddpm_tensor* out, int
     if (!tensor_ok(x) || !tensor_ok(out) || out->H != 2 * x->H || out->W != 2 * x->W || out->C != x->C || out->N != x->N) return DDPM_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
 #define GO(T, VEC) { UpFwd<T, VEC> f{TV(*x), TV(*out)}; int64_t tot = (int64_t)out->N * out->H * out->W * (out->C / VEC); \
-        pix_kernel<T, VEC><<<pix_grid(tot), NT, 0, st>>>(out->N, out->H, out->W, out->C, f); }
+        if (launch_pdl(pix_kernel<T, VEC, decltype(f)>, dim3(pix_grid(tot)), dim3(NT), 0, st, out->N, out->H, out->W, out->C, f) != cudaSuccess) return (int)cudaGetLastError(); }
     if (dtype == DDPM_BF16) { if (vec_ok(x, 8, 2) && vec_ok(out, 8, 2)) GO(bf16, 8) else GO(bf16, 1) }
     else if (dtype == DDPM_F32) { if (vec_ok(x, 4, 4) && vec_ok(out, 4, 4)) GO(float, 4) else GO(float, 1) }
     else return DDPM_E_ARG;
@@ -613,7 +617,7 @@ extern "C" int ddpm_upsample2x_bwd(const ddpm_tensor* dy, const ddpm_tensor* dx,
     if (!tensor_ok(dy) || !tensor_ok(dx) || dy->H != 2 * dx->H || dy->W != 2 * dx->W || dy->C != dx->C || dy->N != dx->N) return DDPM_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
 #define GO(T, VEC) { UpBwd<T, VEC> f{TV(*dy), TV(*dx), accumulate}; int64_t tot = (int64_t)dx->N * dx->H * dx->W * (dx->C / VEC); \
-        pix_kernel<T, VEC><<<pix_grid(tot), NT, 0, st>>>(dx->N, dx->H, dx->W, dx->C, f); }
+        if (launch_pdl(pix_kernel<T, VEC, decltype(f)>, dim3(pix_grid(tot)), dim3(NT), 0, st, dx->N, dx->H, dx->W, dx->C, f) != cudaSuccess) return (int)cudaGetLastError(); }
     if (dtype == DDPM_BF16) { if (vec_ok(dy, 8, 2) && vec_ok(dx, 8, 2)) GO(bf16, 8) else GO(bf16, 1) }
     else if (dtype == DDPM_F32) { if (vec_ok(dy, 4, 4) && vec_ok(dx, 4, 4)) GO(float, 4) else GO(float, 1) }
     else return DDPM_E_ARG;
@@ -638,7 +642,7 @@ extern "C" int ddpm_zero_upsample2x(const ddpm_tensor* x, const ddpm_tensor* out
     if (!tensor_ok(x) || !tensor_ok(out) || out->H != 2 * x->H || out->W != 2 * x->W || out->C != x->C || out->N != x->N) return DDPM_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
 #define GO(T, VEC) { ZeroUp<T, VEC> f{TV(*x), TV(*out)}; int64_t tot = (int64_t)out->N * out->H * out->W * (out->C / VEC); \
-        pix_kernel<T, VEC><<<pix_grid(tot), NT, 0, st>>>(out->N, out->H, out->W, out->C, f); }
+        if (launch_pdl(pix_kernel<T, VEC, decltype(f)>, dim3(pix_grid(tot)), dim3(NT), 0, st, out->N, out->H, out->W, out->C, f) != cudaSuccess) return (int)cudaGetLastError(); }
     if (dtype == DDPM_BF16) { if (vec_ok(x, 8, 2) && vec_ok(out, 8, 2)) GO(bf16, 8) else GO(bf16, 1) }
     else if (dtype == DDPM_F32) { if (vec_ok(x, 4, 4) && vec_ok(out, 4, 4)) GO(float, 4) else GO(float, 1) }
     else return DDPM_E_ARG;
@@ -664,7 +668,7 @@ extern "C" int ddpm_add(const ddpm_tensor* a, const ddpm_tensor* b, const ddpm_t
     if (b->N != out->N || b->H != out->H || b->W != out->W || b->C != out->C) return DDPM_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
 #define GO(T, VEC) { AddOp<T, VEC> f{TV(*a), TV(*b), TV(*out)}; int64_t tot = (int64_t)out->N * out->H * out->W * (out->C / VEC); \
-        pix_kernel<T, VEC><<<pix_grid(tot), NT, 0, st>>>(out->N, out->H, out->W, out->C, f); }
+        if (launch_pdl(pix_kernel<T, VEC, decltype(f)>, dim3(pix_grid(tot)), dim3(NT), 0, st, out->N, out->H, out->W, out->C, f) != cudaSuccess) return (int)cudaGetLastError(); }
     if (dtype == DDPM_BF16) { if (vec_ok(a, 8, 2) && vec_ok(b, 8, 2) && vec_ok(out, 8, 2)) GO(bf16, 8) else GO(bf16, 1) }
     else if (dtype == DDPM_F32) { if (vec_ok(a, 4, 4) && vec_ok(b, 4, 4) && vec_ok(out, 4, 4)) GO(float, 4) else GO(float, 1) }
     else return DDPM_E_ARG;
@@ -677,6 +681,7 @@ extern "C" int ddpm_add(const ddpm_tensor* a, const ddpm_tensor* b, const ddpm_t
 template <typename T, int VEC>
 __global__ void __launch_bounds__(NT) colsum_kernel(TV dy, float* out_nc, float* dbias) {
     extern __shared__ float acc[];           // [C]
+    pdl_enter();
     const int n = blockIdx.y, C = dy.C, HW = dy.H * dy.W;
     for (int c = threadIdx.x; c < C; c += NT) acc[c] = 0.f;
     __syncthreads();
@@ -711,7 +716,7 @@ extern "C" int ddpm_colsum(const ddpm_tensor* dy, int dtype, float* out_nc, floa
     int HW = dy->H * dy->W;
 #define GO(T, VEC) { int cvs = dy->C / VEC; if (cvs > NT) return DDPM_E_ARG; int ppi = NT / cvs; \
         dim3 grid(blocks_per_image(dy->N, HW, ppi * 8), dy->N); \
-        colsum_kernel<T, VEC><<<grid, NT, sizeof(float) * dy->C, st>>>(v, out_nc, dbias); }
+        if (launch_pdl(colsum_kernel<T, VEC>, grid, dim3(NT), sizeof(float) * dy->C, st, v, out_nc, dbias) != cudaSuccess) return (int)cudaGetLastError(); }
     if (dtype == DDPM_BF16) { if (vec_ok(dy, 8, 2)) GO(bf16, 8) else GO(bf16, 1) }
     else if (dtype == DDPM_F32) { if (vec_ok(dy, 4, 4)) GO(float, 4) else GO(float, 1) }
     else return DDPM_E_ARG;

@@ -165,6 +165,9 @@ int ddpm_set_tc_mode(int mode, int base_offset);
 /* 1 (default): persistent CTA-pair kernel (tcgen05 cta_group::2, TMEM double buffering); 0: the
  * first-generation one-tile-per-CTA kernel (kept for A/B measurements) */
 int ddpm_set_tc_v2(int on);
+/* 1 (default; env DDPM_B200_PDL=0 disables): kernels are launched with programmatic stream serialisation
+ * (griddepcontrol): the prologue of kernel i+1 overlaps the tail of kernel i.  0: plain stream order (A/B hook). */
+int ddpm_set_pdl(int on);
 
 /* All time_proj linears of a UNet in one launch (unet_backbone.py:25-27,41): out[m][col0_i + n] =
  * sum_k f(x[m][k]) W_i[n][k] + b_i[n], f = SiLU when a_silu.  `entries_dev` is an array in DEVICE memory. */

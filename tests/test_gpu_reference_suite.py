@@ -285,6 +285,7 @@ def test_checkpoint_round_trip_restores_fused_state(tmp_path):
     data = _loader(4, 4)
     _, _, _, gs = train_one_epoch(model, d, data[:2], opt, scaler=scaler, ema=ema, device="cuda:0")
     save_ckpt(str(tmp_path / "a.pt"), model, opt, scaler, ema, step=gs)
+    w_ck = [p.detach().clone() for p in model.parameters()]
     torch.manual_seed(11)
     ref = train_one_epoch(model, d, data[2:], opt, scaler=scaler, ema=ema, device="cuda:0", global_step=gs)
     w_ref = [p.detach().clone() for p in model.parameters()]
@@ -294,5 +295,19 @@ def test_checkpoint_round_trip_restores_fused_state(tmp_path):
     torch.manual_seed(11)
     again = train_one_epoch(model, d, data[2:], opt, scaler=scaler, ema=ema, device="cuda:0", global_step=gs)
     assert abs(again[0] - ref[0]) < 1e-4 * abs(ref[0])
-    for a, b in zip(w_ref, model.parameters()):
-        assert torch.allclose(a, b.detach(), rtol=1e-4, atol=1e-6)
+    # Run-to-run the result is reproducible but not always bit-identical: fp32 atomics (GroupNorm dgamma/dbeta, bias
+    # column sums) reorder (1e-7 relative on those gradients; tensor-core gradients are bit-stable --
+    # tools/determinism_check.py), and one flipped bf16 rounding downstream is a 4e-3 relative change of that
+    # activation.  So the bar is relative to the distance the two steps moved the weights: restored runs agree to a
+    # small fraction of it, while a run whose Adam moments were NOT restored (negative control below) does not.
+    def dist(u, v):
+        return float(sum(((a.double() - b.double()) ** 2).sum() for a, b in zip(u, v)) ** 0.5)
+    w_again = [p.detach().clone() for p in model.parameters()]
+    moved = dist(w_ref, w_ck)
+    assert moved > 0 and dist(w_again, w_ref) <= 0.1 * moved, (dist(w_again, w_ref), moved)
+    # negative control: same weights / scaler / EMA, fresh optimiser state
+    load_ckpt(str(tmp_path / "a.pt"), model, opt, scaler, ema, map_location="cuda:0")
+    opt2 = torch.optim.AdamW(model.parameters(), lr=1e-3)
+    torch.manual_seed(11)
+    train_one_epoch(model, d, data[2:], opt2, scaler=scaler, ema=ema, device="cuda:0", global_step=gs)
+    assert dist([p.detach() for p in model.parameters()], w_ref) > 0.3 * moved
