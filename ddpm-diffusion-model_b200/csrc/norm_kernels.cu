@@ -11,6 +11,7 @@
 #include "common.cuh"
 
 #include <cooperative_groups.h>
+#include <unordered_map>
 namespace cg = cooperative_groups;
 
 #define NT 256
@@ -83,6 +84,73 @@ static inline int blocks_per_image(int N, int HW, int ppi) {
     int maxb = (HW + ppi - 1) / ppi;
     if (want < 1) want = 1;
     return want < maxb ? want : maxb;
+}
+
+// ---- per-thread cp.async pipeline ---------------------------------------------------------------------------
+// ncu on the register-staged version: 48-60 % issue utilisation with `long_scoreboard` as the top stall and ~30 %
+// achieved occupancy -- each warp alternated "U loads, wait a DRAM round trip, ~150 instructions per packet", so
+// the bytes in flight per SM were far below what HBM latency x bandwidth needs.  Here every thread streams the
+// 16-byte packets it will consume GN_PIPE_D-1 iterations later into its OWN shared-memory slots (LDGSTS, L2 only):
+// no registers are held by loads in flight, no barriers (a thread only reads what it copied itself; completion
+// through cp.async.wait_group), and 1024 threads x 3 iterations x 16-48 B stay in flight per SM.
+#ifndef GN_PIPE_D
+#define GN_PIPE_D 4               // power of two
+#endif
+__device__ __forceinline__ uint32_t sm_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+template <int VEC, int NTEN> constexpr int gn_ring_bytes() {
+    // the ring doubles as the [2*VEC][NT] float scratch of cta_channel_reduce (used only between streaming loops)
+    return VEC == 1 ? 2 * NT * 4 : (GN_PIPE_D * NTEN * NT * 16 > 2 * VEC * NT * 4 ? GN_PIPE_D * NTEN * NT * 16 : 2 * VEC * NT * 4);
+}
+// Calls body(p, r) for p = first, first+step, ... < end with r[t] = the 16-byte packet of tensor t (t < nten <= NTEN)
+// at pixel p, addr(t, p) giving its global address.  VEC == 1 (unaligned fallbacks) loads directly.
+template <typename T, int VEC, int NTEN, typename AddrF, typename BodyF>
+__device__ __forceinline__ void stream_packets(unsigned char* ring, int nten, int first, int end, int step, AddrF addr, BodyF body) {
+    if constexpr (VEC == 1) {
+        for (int p = first; p < end; p += step) {
+            Raw<T, VEC> r[NTEN];
+#pragma unroll
+            for (int t = 0; t < NTEN; ++t) if (t < nten) ldraw<T, VEC>(addr(t, p), r[t]);
+            body(p, r);
+        }
+    } else {
+        constexpr int D = GN_PIPE_D;
+        const uint32_t base = sm_u32(ring) + threadIdx.x * 16u;
+        int pi = first;
+#pragma unroll
+        for (int d = 0; d < D - 1; ++d) {
+            if (pi < end) {
+#pragma unroll
+                for (int t = 0; t < NTEN; ++t) if (t < nten) cp_async16(base + (uint32_t)((d * NTEN + t) * NT * 16), addr(t, pi));
+            }
+            cp_async_commit(); pi += step;
+        }
+        int st = 0;
+        for (int p = first; p < end; p += step) {
+            const int sf = (st + D - 1) & (D - 1);               // the slot the previous iteration consumed
+            if (pi < end) {
+#pragma unroll
+                for (int t = 0; t < NTEN; ++t) if (t < nten) cp_async16(base + (uint32_t)((sf * NTEN + t) * NT * 16), addr(t, pi));
+            }
+            cp_async_commit(); pi += step;
+            cp_async_wait<D - 1>();                              // this iteration's group has landed
+            Raw<T, VEC> r[NTEN];
+#pragma unroll
+            for (int t = 0; t < NTEN; ++t) if (t < nten) r[t].q = lds128(base + (uint32_t)((st * NTEN + t) * NT * 16));
+            body(p, r);
+            st = (st + 1) & (D - 1);
+        }
+        cp_async_wait<0>();
+    }
 }
 
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
@@ -161,12 +229,14 @@ template <typename T, int VEC, int MODE>
 __global__ void __launch_bounds__(NT, GN_FWD_OCC) gn_fwd_kernel(GnP a) {
     extern __shared__ __align__(16) unsigned char gsm[];
     pdl_enter();
-    const int C = a.x.C, G = a.G, cpg = C / G, HW = a.x.H * a.x.W, W = a.x.W;
-    double* chan = reinterpret_cast<double*>(gsm);           // [2][C]
+    const int C = a.x.C, G = a.G, cpg = C / G, HW = a.x.H * a.x.W;
+    constexpr int RING = gn_ring_bytes<VEC, 1>();
+    unsigned char* ring = gsm;
+    float (*part)[NT] = reinterpret_cast<float (*)[NT]>(gsm);    // aliases the ring (see gn_ring_bytes)
+    double* chan = reinterpret_cast<double*>(gsm + RING);     // [2][C]
     double* gpart = chan + 2 * C;                            // [2][G]  (read by the other CTAs of the cluster)
     float* gm = reinterpret_cast<float*>(gpart + 2 * G);     // [G] mean
     float* gr = gm + G;                                      // [G] rstd
-    __shared__ float part[2 * VEC][NT];
     cg::cluster_group cl = cg::this_cluster();
     const int CS = (int)cl.num_blocks(), rank = (int)cl.block_rank();
     const int n = blockIdx.x / CS;
@@ -179,31 +249,20 @@ __global__ void __launch_bounds__(NT, GN_FWD_OCC) gn_fwd_kernel(GnP a) {
     const PixAddr ax(a.x, a.wshift), ao(a.o, a.wshift);
     const T* xb = img_origin<T>(a.x, n, c0);
     T* ob = img_origin<T>(a.o, n, c0);
-    constexpr int U = GN_FWD_U;
+    const int pend = m.active ? p1 : 0;
+    auto xaddr = [&](int, int p) { return ax.at(xb, p); };
 
     if (MODE != 2) {
         float acc[2 * VEC];
 #pragma unroll
         for (int i = 0; i < 2 * VEC; ++i) acc[i] = 0.f;
-        if (m.active) {
-            for (int pb = p0 + m.prow; pb < p1; pb += U * m.ppi) {
-                Raw<T, VEC> r[U];
+        stream_packets<T, VEC, 1>(ring, 1, p0 + m.prow, pend, m.ppi, xaddr, [&](int, Raw<T, VEC>* r) {
+            float v[VEC];
+            unraw<T, VEC>(r[0], v);
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int p = pb + u * m.ppi;
-                    if (p < p1) ldraw<T, VEC>(ax.at(xb, p), r[u]);
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    if (pb + u * m.ppi < p1) {
-                        float v[VEC];
-                        unraw<T, VEC>(r[u], v);
-#pragma unroll
-                        for (int i = 0; i < VEC; ++i) { acc[i] += v[i]; acc[VEC + i] = fmaf(v[i], v[i], acc[VEC + i]); }
-                    }
-                }
-            }
-        }
+            for (int i = 0; i < VEC; ++i) { acc[i] += v[i]; acc[VEC + i] = fmaf(v[i], v[i], acc[VEC + i]); }
+        });
+        __syncthreads();                                     // every thread is done with its ring slots (part aliases them)
         cta_channel_reduce<VEC, 2>(part, acc, chan, C, m);
         for (int o = threadIdx.x; o < 2 * G; o += NT) {
             const int st = o / G, g = o - st * G;
@@ -243,29 +302,17 @@ __global__ void __launch_bounds__(NT, GN_FWD_OCC) gn_fwd_kernel(GnP a) {
             sc[i] = gr[g] * __ldg(a.gamma + c);
             sh[i] = __ldg(a.beta + c) - gm[g] * sc[i];
         }
-        for (int pb = p0 + m.prow; pb < p1; pb += U * m.ppi) {
-            Raw<T, VEC> r[U];
+        stream_packets<T, VEC, 1>(ring, 1, p0 + m.prow, p1, m.ppi, xaddr, [&](int p, Raw<T, VEC>* r) {
+            float v[VEC];
+            unraw<T, VEC>(r[0], v);
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int p = pb + u * m.ppi;
-                if (p < p1) ldraw<T, VEC>(ax.at(xb, p), r[u]);
+            for (int i = 0; i < VEC; ++i) {
+                const float z = fmaf(v[i], sc[i], sh[i]);
+                v[i] = a.act ? silu_f(z) : z;
             }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int p = pb + u * m.ppi;
-                if (p < p1) {
-                    float v[VEC];
-                    unraw<T, VEC>(r[u], v);
-#pragma unroll
-                    for (int i = 0; i < VEC; ++i) {
-                        const float z = fmaf(v[i], sc[i], sh[i]);
-                        v[i] = a.act ? silu_f(z) : z;
-                    }
-                    if (a.thr16) dropout_apply<VEC>(v, dkey, ebase + (uint32_t)p * (uint32_t)C, a.thr16, a.keep_scale);
-                    stv<T, VEC>(ao.at(ob, p), v);
-                }
-            }
-        }
+            if (a.thr16) dropout_apply<VEC>(v, dkey, ebase + (uint32_t)p * (uint32_t)C, a.thr16, a.keep_scale);
+            stv<T, VEC>(ao.at(ob, p), v);
+        });
     }
     if (MODE != 2) cluster_wait();                           // do not exit while peers may still read gpart
 }
@@ -278,13 +325,15 @@ __global__ void __launch_bounds__(NT, STASH ? GN_BWD_OCC : 2) gn_bwd_kernel(GnP 
     extern __shared__ __align__(16) unsigned char gsm[];
     pdl_enter();
     const int C = a.x.C, G = a.G, cpg = C / G, HW = a.x.H * a.x.W;
-    double* chan = reinterpret_cast<double*>(gsm);           // [2][C] this CTA's per-channel partials (read by peers)
+    constexpr int RING = gn_ring_bytes<VEC, 3>();
+    unsigned char* ring = gsm;
+    float (*part)[NT] = reinterpret_cast<float (*)[NT]>(gsm);    // aliases the ring (see gn_ring_bytes)
+    double* chan = reinterpret_cast<double*>(gsm + RING);    // [2][C] this CTA's per-channel partials (read by peers)
     float* tot = reinterpret_cast<float*>(chan + 2 * C);     // [2][C] cluster totals
     float* gA = tot + 2 * C;                                 // [G]
     float* gB = gA + G;                                      // [G]
     float* gm = gB + G;                                      // [G] mean
     float* gr = gm + G;                                      // [G] rstd
-    __shared__ float part[2 * VEC][NT];
     cg::cluster_group cl = cg::this_cluster();
     const int CS = (int)cl.num_blocks(), rank = (int)cl.block_rank();
     const int n = blockIdx.x / CS;
@@ -298,7 +347,8 @@ __global__ void __launch_bounds__(NT, STASH ? GN_BWD_OCC : 2) gn_bwd_kernel(GnP 
     const T* xb = img_origin<T>(a.x, n, c0);
     T* db = img_origin<T>(a.dy, n, c0);
     T* ob = img_origin<T>(a.o, n, c0);
-    constexpr int U = GN_BWD_U;
+    const int pend = m.active ? p1 : 0;
+    auto addr = [&](int t, int p) -> const T* { return t == 0 ? ax.at(xb, p) : (t == 1 ? ad.at(db, p) : ao.at(ob, p)); };
 
     for (int g = threadIdx.x; g < G; g += NT) {
         const double s = a.stats[((size_t)n * G + g) * 2], q = a.stats[((size_t)n * G + g) * 2 + 1];
@@ -321,33 +371,20 @@ __global__ void __launch_bounds__(NT, STASH ? GN_BWD_OCC : 2) gn_bwd_kernel(GnP 
         float acc[2 * VEC];
 #pragma unroll
         for (int i = 0; i < 2 * VEC; ++i) acc[i] = 0.f;
-        if (m.active) {
-            for (int pb = p0 + m.prow; pb < p1; pb += U * m.ppi) {
-                Raw<T, VEC> rx[U], rd[U];
+        stream_packets<T, VEC, 2>(ring, 2, p0 + m.prow, pend, m.ppi, addr, [&](int p, Raw<T, VEC>* r) {
+            float v[VEC], d[VEC];
+            unraw<T, VEC>(r[0], v); unraw<T, VEC>(r[1], d);
+            if (a.thr16) dropout_apply<VEC>(d, dkey, ebase + (uint32_t)p * (uint32_t)C, a.thr16, a.keep_scale);
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int p = pb + u * m.ppi;
-                    if (p < p1) { ldraw<T, VEC>(ax.at(xb, p), rx[u]); ldraw<T, VEC>(ad.at(db, p), rd[u]); }
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int p = pb + u * m.ppi;
-                    if (p < p1) {
-                        float v[VEC], d[VEC];
-                        unraw<T, VEC>(rx[u], v); unraw<T, VEC>(rd[u], d);
-                        if (a.thr16) dropout_apply<VEC>(d, dkey, ebase + (uint32_t)p * (uint32_t)C, a.thr16, a.keep_scale);
-#pragma unroll
-                        for (int i = 0; i < VEC; ++i) {
-                            float dz = d[i];
-                            if (a.act) dz *= dsilu_f(fmaf(v[i], sc[i], sh[i]));
-                            acc[i] += dz; acc[VEC + i] = fmaf(dz, v[i], acc[VEC + i]);
-                            d[i] = dz;
-                        }
-                        if (STASH) stv<T, VEC>(ad.at(db, p), d);
-                    }
-                }
+            for (int i = 0; i < VEC; ++i) {
+                float dz = d[i];
+                if (a.act) dz *= dsilu_f(fmaf(v[i], sc[i], sh[i]));
+                acc[i] += dz; acc[VEC + i] = fmaf(dz, v[i], acc[VEC + i]);
+                d[i] = dz;
             }
-        }
+            if (STASH) stv<T, VEC>(ad.at(db, p), d);
+        });
+        __syncthreads();                                     // every thread is done with its ring slots (part aliases them)
         cta_channel_reduce<VEC, 2>(part, acc, chan, C, m);
     }
     cluster_arrive(); cluster_wait();                        // every CTA's chan[] is complete
@@ -389,46 +426,31 @@ __global__ void __launch_bounds__(NT, STASH ? GN_BWD_OCC : 2) gn_bwd_kernel(GnP 
             k0[i] = r_ * g_; k1[i] = r_ * r_ * gB[g]; k2[i] = m_ * r_ * gB[g] - r_ * gA[g];
             rs[i] = r_; mr[i] = m_; ga[i] = g_; be[i] = __ldg(a.beta + c);      // only used when !STASH
         }
-        for (int pb = p0 + m.prow; pb < p1; pb += U * m.ppi) {
-            Raw<T, VEC> rx[U], rd[U], ro[U];
+        stream_packets<T, VEC, 3>(ring, a.accumulate ? 3 : 2, p0 + m.prow, p1, m.ppi, addr, [&](int p, Raw<T, VEC>* rw) {
+            float v[VEC], d[VEC], r[VEC];
+            unraw<T, VEC>(rw[0], v); unraw<T, VEC>(rw[1], d);
+            if (a.accumulate) unraw<T, VEC>(rw[2], r);
+            if (!STASH) {                                          // recompute dz (phase 1 could not leave it in dy)
+                if (a.thr16) dropout_apply<VEC>(d, dkey, ebase + (uint32_t)p * (uint32_t)C, a.thr16, a.keep_scale);
+                if (a.act) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int p = pb + u * m.ppi;
-                if (p < p1) {
-                    ldraw<T, VEC>(ax.at(xb, p), rx[u]);
-                    ldraw<T, VEC>(ad.at(db, p), rd[u]);
-                    if (a.accumulate) ldraw<T, VEC>(ao.at(ob, p), ro[u]);
+                    for (int i = 0; i < VEC; ++i) d[i] *= dsilu_f(fmaf(fmaf(v[i], rs[i], -mr[i]), ga[i], be[i]));
                 }
             }
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int p = pb + u * m.ppi;
-                if (p < p1) {
-                    float v[VEC], d[VEC], r[VEC];
-                    unraw<T, VEC>(rx[u], v); unraw<T, VEC>(rd[u], d);
-                    if (a.accumulate) unraw<T, VEC>(ro[u], r);
-                    if (!STASH) {                                          // recompute dz (phase 1 could not leave it in dy)
-                        if (a.thr16) dropout_apply<VEC>(d, dkey, ebase + (uint32_t)p * (uint32_t)C, a.thr16, a.keep_scale);
-                        if (a.act) {
-#pragma unroll
-                            for (int i = 0; i < VEC; ++i) d[i] *= dsilu_f(fmaf(fmaf(v[i], rs[i], -mr[i]), ga[i], be[i]));
-                        }
-                    }
-#pragma unroll
-                    for (int i = 0; i < VEC; ++i) {
-                        const float g = fmaf(-v[i], k1[i], fmaf(d[i], k0[i], k2[i]));
-                        r[i] = a.accumulate ? r[i] + g : g;
-                        csum[i] += r[i];
-                    }
-                    stv<T, VEC>(ao.at(ob, p), r);
-                }
+            for (int i = 0; i < VEC; ++i) {
+                const float g = fmaf(-v[i], k1[i], fmaf(d[i], k0[i], k2[i]));
+                r[i] = a.accumulate ? r[i] + g : g;
+                csum[i] += r[i];
             }
-        }
+            stv<T, VEC>(ao.at(ob, p), r);
+        });
     }
     cluster_wait();                                          // peers are done with chan[] -> it can be reused
     if (a.cs_nc || a.cs_c) {
         // fused column sums of dx: the bias gradient of the convolution that produced x and the
         // per-image time-bias gradient (replaces a separate pass over dx, ddpm_colsum)
+        __syncthreads();                                     // ring slots are dead before part[] is written
         cta_channel_reduce<VEC, 1>(part, csum, chan, C, m);
         for (int c = threadIdx.x; c < C; c += NT) {
             const float v = (float)chan[c];
@@ -449,6 +471,15 @@ static int log2_exact(int v) { int s = 0; while ((1 << s) < v) ++s; return (1 <<
 
 template <typename K>
 static int launch_cluster(K kernel, int grid, int cs, size_t smem, cudaStream_t st, GnP& p) {
+    if (smem > 48 * 1024) {                                  // once per kernel instantiation (all share the type K)
+        static std::unordered_map<const void*, size_t> configured;
+        size_t& have = configured[(const void*)kernel];
+        if (smem > have) {
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+            have = smem;
+        }
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute at[2]; unsigned nat = 1;
@@ -477,11 +508,11 @@ static int gn_fill(GnP& p, const ddpm_tensor* x, int groups, const double* stats
 template <int MODE>
 static int gn_fwd_dispatch(GnP& p, const ddpm_tensor* x, const ddpm_tensor* out, int dtype, cudaStream_t st) {
     const int HW = x->H * x->W, C = x->C, G = p.G;
-    const size_t sm = sizeof(double) * (2 * C + 2 * G) + sizeof(float) * 2 * G;
+    const size_t sm0 = sizeof(double) * (2 * C + 2 * G) + sizeof(float) * 2 * G;
 #define GO(T, VEC) { int cvs = C / VEC; if (cvs > NT) return DDPM_E_ARG; \
         int cs = MODE == 2 ? 1 : gn_cluster_size(HW, cvs); \
         if (MODE == 2) { cs = 1; int want = (HW * cvs) / (NT * 16); while (cs < 8 && cs < want) cs <<= 1; } \
-        return launch_cluster(gn_fwd_kernel<T, VEC, MODE>, x->N * cs, cs, sm, st, p); }
+        return launch_cluster(gn_fwd_kernel<T, VEC, MODE>, x->N * cs, cs, sm0 + gn_ring_bytes<VEC, 1>(), st, p); }
     const bool v8 = vec_ok(x, 8, 2) && (MODE == 1 || vec_ok(out, 8, 2));
     const bool v4 = vec_ok(x, 4, 4) && (MODE == 1 || vec_ok(out, 4, 4));
     if (dtype == DDPM_BF16) { if (v8) GO(bf16, 8) else GO(bf16, 1) }
@@ -530,8 +561,9 @@ static int gn_bwd_impl(const ddpm_tensor* x, int dtype, int groups, const double
     cudaStream_t st = (cudaStream_t)stream;
     if (cs_nc) CUDA_TRY(cudaMemsetAsync(cs_nc, 0, sizeof(float) * x->N * x->C, st));
     const int HW = x->H * x->W, C = x->C;
-    const size_t sm = sizeof(double) * 2 * C + sizeof(float) * (2 * C + 4 * groups);
+    const size_t sm0 = sizeof(double) * 2 * C + sizeof(float) * (2 * C + 4 * groups);
 #define GO(T, VEC) { int cvs = C / VEC; if (cvs > NT) return DDPM_E_ARG; int cs = gn_cluster_size(HW, cvs); \
+        const size_t sm = sm0 + gn_ring_bytes<VEC, 3>(); \
         if (p.stash) return launch_cluster(gn_bwd_kernel<T, VEC, true>, x->N * cs, cs, sm, st, p); \
         return launch_cluster(gn_bwd_kernel<T, VEC, false>, x->N * cs, cs, sm, st, p); }
     if (dtype == DDPM_BF16) { if (vec_ok(x, 8, 2) && vec_ok(dy, 8, 2) && vec_ok(dx, 8, 2)) GO(bf16, 8) else GO(bf16, 1) }
