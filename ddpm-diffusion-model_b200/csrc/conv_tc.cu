@@ -922,10 +922,21 @@ struct WgTcParams {
     float* dbias;               // fp32 [CoutV], accumulated by the reduce kernel
     float* dw;                  // fp32 OIHW gradient; non-NULL: cooperative launch, the split-K partials are reduced
                                 // by the same kernel behind a grid barrier (no second launch)
+    int cl3;                    // 1: the three filter-row CTAs of a (split, ci tile, co tile) form a cluster (1,3,1) and
+                                //    share ONE multicast TMA load of the dY tile (L2->SM traffic of dY / 3)
 };
 
 __device__ __forceinline__ void wgrad_reduce_body(const float* __restrict__ ws, float* __restrict__ dw, int splits, const WgTcParams& p,
                                                   int gtid, int gthreads);
+// one load, delivered to the same shared-memory offset (and signalling the same barrier offset) in every CTA of `mask`
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, uint16_t mask) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+                 ::"r"(smem_u32(dst)), "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {      // arrives on `bar` in every CTA of `mask`
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
 __global__ void __launch_bounds__(TC_THREADS) wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY,
                                                                const __grid_constant__ CUtensorMap tmA, WgTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -936,12 +947,16 @@ __global__ void __launch_bounds__(TC_THREADS) wgrad_tc_kernel(const __grid_const
     uint64_t* acc_full = empty + WG_STAGES;
     uint32_t* tmem_slot = (uint32_t*)(acc_full + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int split = blockIdx.x, grp = blockIdx.y, mtile = blockIdx.z;
+    const int split = blockIdx.x, mtile = blockIdx.z;
+    // cluster mode: blockIdx.y = ntile * 3 + ky, so that the cluster (1,3,1) holds the three filter rows of one ci tile
+    const uint32_t crank = p.cl3 ? cluster_ctarank() : 0u;
+    const int ky = p.cl3 ? (int)crank : (int)blockIdx.y / p.n_tiles;
+    const int ntile = p.cl3 ? (int)blockIdx.y / 3 : (int)blockIdx.y - ky * p.n_tiles;
+    const int grp = ky * p.n_tiles + ntile;                     // workspace / bias-dealing index (same in both modes)
     // the K-steps of the bias reduction are dealt round-robin to the gridDim.y groups that stream the same dY
     // rows (putting all of them on group 0 made those CTAs the critical path: +11..16 % kernel time)
     const bool do_bias = p.ws_bias != nullptr;
     const int ngrp = gridDim.y;
-    const int ky = grp / p.n_tiles, ntile = grp - ky * p.n_tiles;
     const int m0 = mtile * 128, n0 = ntile * p.NT;
     const int s_beg = split * p.stages_per_cta;
     const int s_end = min(p.stages_total, s_beg + p.stages_per_cta);
@@ -949,7 +964,9 @@ __global__ void __launch_bounds__(TC_THREADS) wgrad_tc_kernel(const __grid_const
     const int y_bytes = 2 * WG_KQ * 128;                 // two 64-channel blocks of dY
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < WG_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        // cluster mode: rank 0 multicasts dY into all three CTAs, so ITS empty[s] collects the release of all three
+        // MMA warps (the others' commits arrive remotely); ranks 1, 2 only wait for their own
+        for (int i = 0; i < WG_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], (p.cl3 && crank == 0) ? 3 : 1); }
         mbar_init(acc_full, 1);
         fence_barrier_init();
     }
@@ -960,6 +977,7 @@ __global__ void __launch_bounds__(TC_THREADS) wgrad_tc_kernel(const __grid_const
     }
     tc_fence_before();
     __syncthreads();
+    if (p.cl3) cluster_sync_all();                       // peers' barriers are initialised before anyone signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t bias_col = (uint32_t)(p.ntap * p.NT);
@@ -973,8 +991,13 @@ __global__ void __launch_bounds__(TC_THREADS) wgrad_tc_kernel(const __grid_const
                 uint8_t* dst = smem + (size_t)s * p.stage_bytes;
                 mbar_expect_tx(&full[s], (uint32_t)(y_bytes + p.nblkA * WG_ROWS * 128));
                 const int Q = (s_beg + i) * WG_KQ;
-                tma_load_2d(dst, &tmY, &full[s], m0, Q);
-                tma_load_2d(dst + WG_KQ * 128, &tmY, &full[s], m0 + 64, Q);
+                if (!p.cl3) {
+                    tma_load_2d(dst, &tmY, &full[s], m0, Q);
+                    tma_load_2d(dst + WG_KQ * 128, &tmY, &full[s], m0 + 64, Q);
+                } else if (crank == 0) {                 // every CTA armed / will arm its own full[s] with the same byte count
+                    tma_load_2d_mc(dst, &tmY, &full[s], m0, Q, (uint16_t)7);
+                    tma_load_2d_mc(dst + WG_KQ * 128, &tmY, &full[s], m0 + 64, Q, (uint16_t)7);
+                }
                 const int rowA = p.ntap == 3 ? Q + (ky - 1) * p.Wp - 1 : Q;
                 for (int b = 0; b < p.nblkA; ++b)
                     tma_load_2d(dst + y_bytes + (size_t)b * WG_ROWS * 128, &tmA, &full[s], n0 + 64 * b, rowA);
@@ -993,6 +1016,7 @@ __global__ void __launch_bounds__(TC_THREADS) wgrad_tc_kernel(const __grid_const
             const bool three = p.ntap == 3;
             const uint32_t idesc_b = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
             const uint64_t ones_desc = desc_pack(desc_lo(smem_u32(ones), 2048u), hi);
+            const uint16_t relmask = (uint16_t)((1u << crank) | 1u);   // release the stage here and at the multicasting rank 0
             // two copies of the loop: a predicated-off bias MMA in the common loop cost 11 % (measured A/B)
             auto run = [&](auto with_bias) {
                 constexpr bool BIAS = decltype(with_bias)::value;
@@ -1017,7 +1041,7 @@ __global__ void __launch_bounds__(TC_THREADS) wgrad_tc_kernel(const __grid_const
                         }
                     }
                     acc = 1;
-                    if (el) umma_commit(&empty[s]);
+                    if (el) { if (p.cl3) umma_commit_mc(&empty[s], relmask); else umma_commit(&empty[s]); }
                     __syncwarp();
                 }
             };
@@ -1057,6 +1081,7 @@ __global__ void __launch_bounds__(TC_THREADS) wgrad_tc_kernel(const __grid_const
         tc_fence_before();
     }
     __syncthreads();
+    if (p.cl3) cluster_sync_all();                       // nobody exits while peers may still signal its barriers
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
     if (p.dw) {
         // split-K reduction in the same (cooperative) launch: every CTA's partial tile is in the workspace after the
@@ -1080,9 +1105,17 @@ __device__ __forceinline__ void wgrad_reduce_body(const float* __restrict__ ws, 
         int mtile = co >> 7, ntile = ci / p.NT;
         size_t off = ((((size_t)mtile) * grps + ky * p.n_tiles + ntile) * 128 + (co & 127)) * cols + kx * p.NT + (ci - ntile * p.NT);
         size_t stride = (size_t)p.m_tiles * grps * 128 * cols;
-        float acc = 0.f;
-        for (int s = 0; s < splits; ++s) acc += ws[off + s * stride];
-        dw[((size_t)co * p.CinV + ci) * taps + tap] += acc;
+        // four independent partial sums: the loads of a thread are independent instead of one dependent chain per
+        // split (the kernel is latency-bound: ~80 k outputs x 12-49 splits); fixed order -> still deterministic
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        const float* w0 = ws + off;
+        int s = 0;
+        for (; s + 4 <= splits; s += 4) {
+            a0 += w0[(size_t)s * stride]; a1 += w0[(size_t)(s + 1) * stride];
+            a2 += w0[(size_t)(s + 2) * stride]; a3 += w0[(size_t)(s + 3) * stride];
+        }
+        for (; s < splits; ++s) a0 += w0[(size_t)s * stride];
+        dw[((size_t)co * p.CinV + ci) * taps + tap] += (a0 + a1) + (a2 + a3);
     }
     if (p.ws_bias && p.dbias) {                              // one warp per output channel, lanes stride over the partials
         const int lane = gtid & 31, nwarp = gthreads >> 5;
@@ -1113,6 +1146,34 @@ static int wg_pick_nt(int Cin) {
     return 0;
 }
 
+static size_t wg_smem_bytes(const WgTcParams& p) { return (size_t)WG_STAGES * p.stage_bytes + 2048 + 8 * (2 * WG_STAGES + 1) + 16 + 1024; }
+static int wg_set_smem(size_t smem) {
+    static size_t configured = 0;
+    if (smem > configured) {
+        CUDA_TRY(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    return 0;
+}
+// how many (1,3,1) clusters of 178 KB CTAs the device holds at once (GPCs whose SM count is not a multiple of 3 leave
+// SMs idle: 48 clusters = 144 of 148 SMs on B200); a grid larger than that would run a second, nearly empty wave
+static int wg_max_clusters(size_t smem) {
+    static size_t key[4] = {0, 0, 0, 0}; static int val[4] = {0, 0, 0, 0};
+    for (int i = 0; i < 4; ++i) if (key[i] == smem) return val[i];
+    int n = 0;
+    if (wg_set_smem(smem) == 0) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(1, 3, 1); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 3; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        if (cudaOccupancyMaxActiveClusters(&n, wgrad_tc_kernel, &cfg) != cudaSuccess) { n = 0; cudaGetLastError(); }
+    }
+    for (int i = 0; i < 4; ++i) if (key[i] == 0) { key[i] = smem; val[i] = n; break; }
+    return n;
+}
+
 static void wg_plan(const ddpm_wgrad_args* a, WgTcParams* p, int* splits) {
     p->Cin = a->act.C; p->Cout = a->dy.C; p->NT = wg_pick_nt(p->Cin);
     p->ntap = a->KH == 3 ? 3 : 1;
@@ -1127,6 +1188,15 @@ static void wg_plan(const ddpm_wgrad_args* a, WgTcParams* p, int* splits) {
     // one CTA per SM (176 KB of shared memory): the grid must not exceed ONE wave, or the second,
     // nearly empty wave doubles the kernel's duration -> floor, not ceil
     int sp = sm_count() / yz;
+    p->cl3 = 0;
+    // Measured: no gain (2.84 vs 2.72 ms of wgrad per step without PDL, and clusters of 178 KB CTAs interact badly with
+    // programmatic dependent launch: 3.65 ms) -- the kernel is bound by the tensor core's SHARED-MEMORY operand reads
+    // (M=128, N=96, K=16: 4 KB + 3 KB per 48-cycle MMA = 146 B/clk against 128 B/clk), not by L2->SM traffic.  Opt-in
+    // through bit 9 of the experiment flags.
+    if (p->ntap == 3 && (g_tc_exp & 512)) {
+        const int mc = wg_max_clusters(wg_smem_bytes(*p));
+        if (mc >= p->n_tiles * p->m_tiles) { p->cl3 = 1; sp = mc / (p->n_tiles * p->m_tiles); }
+    }
     int max_sp = (p->stages_total + 7) / 8; if (max_sp < 1) max_sp = 1;
     if (sp > max_sp) sp = max_sp;
     if (sp < 1) sp = 1;
@@ -1172,16 +1242,12 @@ int wgrad_tc_launch(const ddpm_wgrad_args* a, cudaStream_t st) {
         uint32_t b[2] = {64, WG_ROWS};
         if (encode(&tmA, a->act.ptr, 2, d, s, b, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
     }
-    size_t smem = (size_t)WG_STAGES * p.stage_bytes + 2048 + 8 * (2 * WG_STAGES + 1) + 16 + 1024;
-    static size_t configured = 0;
-    if (smem > configured) {
-        CUDA_TRY(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    size_t smem = wg_smem_bytes(p);
+    rc = wg_set_smem(smem); if (rc) return rc;
     dim3 grid(splits, p.ntap * p.n_tiles, p.m_tiles);
     // In-kernel split-K reduction behind a cooperative grid barrier: measured SLOWER on B200 (a cooperative launch costs
     // ~50 us: 96->96@64 100 -> 153 us), so it stays an experiment (bit 8 of the flags); default = separate reduce kernel.
-    const bool fused = (g_tc_exp & 256) && (int)(grid.x * grid.y * grid.z) <= sm_count();
+    const bool fused = (g_tc_exp & 256) && !p.cl3 && (int)(grid.x * grid.y * grid.z) <= sm_count();
     p.dw = fused ? a->dw : nullptr;
     if (fused) {
         cudaLaunchConfig_t cfg = {};
@@ -1193,7 +1259,18 @@ int wgrad_tc_launch(const ddpm_wgrad_args* a, cudaStream_t st) {
         LAUNCH_OK();
         return 0;
     }
-    CUDA_TRY(launch_pdl(wgrad_tc_kernel, grid, dim3(TC_THREADS), smem, st, tmY, tmA, p));
+    if (p.cl3) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute at[2]; unsigned nat = 1;
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 3; at[0].val.clusterDim.z = 1;
+        pdl_attr(at, &nat);
+        cfg.attrs = at; cfg.numAttrs = nat;
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, wgrad_tc_kernel, tmY, tmA, p));
+    } else {
+        CUDA_TRY(launch_pdl(wgrad_tc_kernel, grid, dim3(TC_THREADS), smem, st, tmY, tmA, p));
+    }
     LAUNCH_OK();
     int total = p.CoutV * p.ntap * p.ntap * p.CinV;
     int rg = (total + 255) / 256; if (rg > 148 * 8) rg = 148 * 8;

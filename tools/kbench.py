@@ -21,6 +21,7 @@ ap.add_argument("--json", default=None)
 ap.add_argument("--epi", action="store_true", help="conv: also time with bias + time-bias + residual epilogue")
 ap.add_argument("--v1", action="store_true", help="conv: also time the first-generation kernel")
 ap.add_argument("--gnshape", default=None, help="restrict gn to one 'C,H'")
+ap.add_argument("--tcexp", type=int, default=0, help="experiment flags for the whole run (ddpm_set_tc_mode(1 | flags << 4)), e.g. 512 = wgrad with (1,3,1) clusters + dY multicast")
 ap.add_argument("--shape", default=None, help="restrict conv/wgrad to one 'Cin,Cout,H' (for ncu)")
 args = ap.parse_args()
 only = set(args.only.split(","))
@@ -110,6 +111,7 @@ if "conv" in only:
         del x, y
 
 if "wgrad" in only:
+    _lib.lib.ddpm_set_tc_mode(1 | (args.tcexp << 4), 0)
     for ci, co, hw, cnt, *kk in CONV:
         w = torch.nn.Parameter(torch.zeros(co, ci, 3, 3, device=dev))
         x = E.act(B, hw, hw, ci); x.interior().normal_()
