@@ -445,6 +445,48 @@ extern "C" int ddpm_to_image01(const float* x, float* out, int64_t n, void* stre
     return launch_ew(f, 1, n, al16(x) && al16(out), (cudaStream_t)stream);
 }
 
+// ---------------------------------------------------------------- image grid + uint8 (sampler output path)
+// torchvision.utils.make_grid(padding, pad_value = 0) and save_image's `mul(255).add_(0.5).clamp_(0,255).to(uint8)` in
+// one pass over the output pixels (ddpm_inference.py:41-45, ddpim_inference.py:90-93): the reference issues one
+// narrow().copy_() launch per image plus four elementwise passes and a permute before the D2H copy.
+__global__ void image_grid_kernel(const float* __restrict__ x, int N, int C, int H, int W, int xmaps, int pad, int Hg, int Wg,
+                                  float* __restrict__ gf, uint8_t* __restrict__ gu) {
+    pdl_enter();
+    const int64_t total = (int64_t)Hg * Wg;
+    const int ch = H + pad, cw = W + pad;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int gy = (int)(i / Wg), gx = (int)(i - (int64_t)gy * Wg);
+        int k = -1, iy = 0, ix = 0;
+        if (N == 1) { k = 0; iy = gy; ix = gx; }                     // make_grid returns a single image unchanged
+        else {
+            const int y = gy - pad, x_ = gx - pad;
+            if (y >= 0 && x_ >= 0) {
+                const int cy = y / ch, cx = x_ / cw;
+                iy = y - cy * ch; ix = x_ - cx * cw;
+                if (iy < H && ix < W && cx < xmaps && cy * xmaps + cx < N) k = cy * xmaps + cx;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float v = k >= 0 ? x[(((int64_t)k * C + (C == 1 ? 0 : c)) * H + iy) * W + ix] : 0.f;
+            if (gf) gf[(int64_t)c * total + i] = v;
+            if (gu) gu[i * 3 + c] = (uint8_t)fminf(fmaxf(__fadd_rn(__fmul_rn(v, 255.f), 0.5f), 0.f), 255.f);
+        }
+    }
+}
+extern "C" int ddpm_image_grid(const float* x01, int N, int C, int H, int W, int nrow, int pad, float* grid_f32,
+                               uint8_t* grid_u8, void* stream) {
+    if (!x01 || N <= 0 || (C != 1 && C != 3) || H <= 0 || W <= 0 || nrow <= 0 || pad < 0 || (!grid_f32 && !grid_u8)) return DDPM_E_ARG;
+    const int xmaps = nrow < N ? nrow : N, ymaps = (N + xmaps - 1) / xmaps;
+    const int Hg = N == 1 ? H : (H + pad) * ymaps + pad, Wg = N == 1 ? W : (W + pad) * xmaps + pad;
+    const int64_t total = (int64_t)Hg * Wg;
+    int grid = (int)((total + 255) / 256); if (grid > 148 * 8) grid = 148 * 8;
+    CUDA_TRY(launch_pdl(image_grid_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, x01, N, C, H, W, xmaps, pad, Hg, Wg,
+                        grid_f32, grid_u8));
+    LAUNCH_OK();
+    return 0;
+}
+
 // ---------------------------------------------------------------- layout conversion
 template <typename TS, typename TD, bool TO_NHWC>
 __global__ void layout_kernel(char* nchw, int64_t sn, int64_t sc, int64_t sh, int64_t sw, TV v, int srcC) {

@@ -4,7 +4,6 @@ import os
 from contextlib import contextmanager
 
 import torch
-import torchvision.utils as vutils
 
 from .. import dist as _dist
 from ..model.difussion_class import to_image01
@@ -89,17 +88,91 @@ def graphs_enabled() -> bool:
     return os.environ.get("DDPM_B200_GRAPHS", "0") == "1"
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# sampler output path: grid assembly + uint8 conversion in one kernel, one pinned D2H copy, PNG
+# encoding off the critical path when asked for
+# ------------------------------------------------------------------------------------------------------------------
+_PNG_LEVEL = int(os.environ.get("DDPM_B200_PNG_LEVEL", "3"))      # zlib level; the decoded pixels are the same at every level
+_WRITER = None
+_PENDING = []
+
+
+def _grid_shape(N, H, W, nrow, pad):
+    if N == 1:
+        return H, W
+    xm = min(nrow, N)
+    return (H + pad) * math.ceil(N / xm) + pad, (W + pad) * xm + pad
+
+
+def image_grid(x01: torch.Tensor, nrow: int, pad: int = 2, want_float: bool = True):
+    """torchvision.make_grid(x01, nrow, padding=pad) as a device fp32 tensor [3,Hg,Wg] and the uint8 HWC image that
+    torchvision.save_image would hand to PIL (pinned host memory, already synchronised).  One kernel + one D2H."""
+    from .. import _lib
+    if x01.dim() == 3:
+        x01 = x01.unsqueeze(0)
+    if not (x01.is_cuda and x01.dim() == 4 and x01.shape[1] in (1, 3)):
+        raise RuntimeError("ddpm_b200.image_grid expects a CUDA tensor [N,1|3,H,W] (no CPU fallback)")
+    x = x01.detach().to(torch.float32).contiguous()
+    N, Cc, H, W = x.shape
+    Hg, Wg = _grid_shape(N, H, W, nrow, pad)
+    grid = torch.empty((3, Hg, Wg), dtype=torch.float32, device=x.device) if want_float else None
+    u8 = torch.empty((Hg, Wg, 3), dtype=torch.uint8, device=x.device)
+    _lib.call("ddpm_image_grid", x.data_ptr(), N, Cc, H, W, int(nrow), int(pad), grid.data_ptr() if want_float else None,
+              u8.data_ptr(), torch.cuda.current_stream(x.device).cuda_stream)
+    host = torch.empty((Hg, Wg, 3), dtype=torch.uint8).pin_memory()
+    host.copy_(u8, non_blocking=True)
+    torch.cuda.current_stream(x.device).synchronize()
+    return grid, host
+
+
+def _encode(arr, path):
+    os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+    if str(path).lower().endswith(".png"):
+        from ._png import encode_png
+        with open(path, "wb") as f:
+            f.write(encode_png(arr, _PNG_LEVEL))
+    else:                                                      # other formats: PIL, like torchvision.save_image
+        from PIL import Image
+        Image.fromarray(arr).save(path)
+
+
+def write_image(host_u8: torch.Tensor, path: str) -> None:
+    """PNG (or whatever the extension says) from an HWC uint8 host tensor.  With DDPM_B200_ASYNC_IO=1 the encoding
+    runs on a writer thread so that a sampling sweep is not serialised behind zlib; `flush_image_writes()` (also
+    registered with atexit) waits for the files."""
+    global _WRITER
+    arr = host_u8.numpy()
+    if os.environ.get("DDPM_B200_ASYNC_IO", "0") == "1":
+        if _WRITER is None:
+            import atexit
+            from concurrent.futures import ThreadPoolExecutor
+            _WRITER = ThreadPoolExecutor(max_workers=2)
+            atexit.register(flush_image_writes)
+        _PENDING.append(_WRITER.submit(_encode, arr, path))
+    else:
+        _encode(arr, path)
+
+
+def flush_image_writes() -> None:
+    while _PENDING:
+        _PENDING.pop().result()
+
+
 def save_grid(x01, nrow, out_path, pad=2):
-    grid = vutils.make_grid(x01, nrow=nrow, padding=pad)
-    os.makedirs(os.path.dirname(out_path) or ".", exist_ok=True)
-    vutils.save_image(grid, out_path)
+    """vutils.make_grid + vutils.save_image of the reference samplers; returns the float grid like they do."""
+    grid, host = image_grid(x01, nrow, pad)
+    write_image(host, out_path)
     return grid
 
 
 def save_each(x01, out_dir):
+    """One file per sample (ddpm_inference.py:47-51): one kernel + one D2H for the whole batch (a vertical stack with no
+    padding is N contiguous HWC images), then one encode per file."""
     os.makedirs(out_dir, exist_ok=True)
-    for i in range(x01.shape[0]):
-        vutils.save_image(x01[i], os.path.join(out_dir, f"img_{i:03d}.png"))
+    N, H = x01.shape[0], x01.shape[2]
+    _, host = image_grid(x01, 1, 0, want_float=False)
+    for i in range(N):
+        write_image(host[i * H:(i + 1) * H], os.path.join(out_dir, f"img_{i:03d}.png"))
 
 
-__all__ = ["sampling_weights", "initial_noise", "save_grid", "save_each", "to_image01", "math"]
+__all__ = ["sampling_weights", "initial_noise", "save_grid", "save_each", "image_grid", "write_image", "flush_image_writes", "to_image01", "math"]

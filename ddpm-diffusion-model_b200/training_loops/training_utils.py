@@ -2,10 +2,10 @@
 import os
 
 import torch
-from torchvision.utils import make_grid, save_image
 from torchvision.utils import save_image as _tv_save_image
 
 from ..model.difussion_class import to_image01
+from ..testing._common import image_grid, write_image
 
 
 def _restore(model, backup):
@@ -26,21 +26,23 @@ def sample_ddpm(model, diffusion, n: int, img_size: int = 64, device="cuda", ste
         t = torch.full((n,), i, device=device, dtype=torch.long)
         x = diffusion.p_sample_step(model, x, t)
     x = to_image01(x)
-    grid = make_grid(x, nrow=int(n ** 0.5), padding=2)
+    grid, host = image_grid(x, int(n ** 0.5), 2)             # make_grid + save_image's uint8 conversion, one kernel
     if save_path is not None:
-        save_image(grid, save_path)
+        write_image(host, save_path)
     return grid if return_grid else x
 
 
 def save_image_grid(x: torch.Tensor, path: str, nrow: int | None = None):
     """training_utils.py:33-50 (with the `os` import the reference forgot)."""
-    x = x.detach().float().cpu()
     if nrow is None:
         nrow = max(1, int(x.size(0) ** 0.5))
     d = os.path.dirname(path)
     if d:
         os.makedirs(d, exist_ok=True)
-    _tv_save_image(x, path, nrow=nrow)
+    if x.is_cuda and x.dim() == 4 and x.shape[1] in (1, 3):
+        write_image(image_grid(x, nrow, 2, want_float=False)[1], path)
+    else:                                                     # host tensors / odd channel counts: torchvision as is
+        _tv_save_image(x.detach().float().cpu(), path, nrow=nrow)
     print(f"[OK] Guardado grid en {path}")
 
 

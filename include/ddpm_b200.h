@@ -77,6 +77,13 @@ int ddpm_ddim_step(void* sched, const float* xt, const void* eps, int eps_dtype,
                    void* stream);
 /* (clamp(x,-1,1)+1)/2: ddpm_inference.py:40, ddpim_inference.py:89 */
 int ddpm_to_image01(const float* x, float* out, int64_t n, void* stream);
+/* Sampler output path: torchvision make_grid(nrow, padding, pad_value 0) of fp32 [N][C][H][W] images
+ * in [0,1] (C = 1 or 3; one channel is replicated) and save_image's uint8 conversion trunc(clamp(v*255 + 0.5, 0, 255))
+ * (ddpm_inference.py:41-45, ddpim_inference.py:90-93) in one pass.  grid_f32: [3][Hg][Wg] or NULL; grid_u8: [Hg][Wg][3]
+ * (what PIL consumes) or NULL; Hg = (H+pad)*ceil(N/min(nrow,N)) + pad, Wg = (W+pad)*min(nrow,N) + pad; N == 1 returns the
+ * image itself (Hg = H, Wg = W), like make_grid. */
+int ddpm_image_grid(const float* x01, int N, int C, int H, int W, int nrow, int pad, float* grid_f32, uint8_t* grid_u8,
+                    void* stream);
 
 /* ---------------- layout at the API boundary (NCHW-shaped, any strides <-> NHWC) ---------- */
 /* dst->C may exceed src_C (channel padding for the tensor-core kernels): the extra channels are

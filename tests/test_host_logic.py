@@ -278,3 +278,20 @@ print("reference-load-ok")
 """
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert "reference-load-ok" in r.stdout, r.stderr[-2000:]
+
+
+def test_png_encoder_round_trips_through_pil():
+    """Sampler output path: the threaded PNG writer decodes to exactly the pixels it was given."""
+    import io
+    import numpy as np
+    from PIL import Image
+    from ddpm_diffusion_model_b200.testing._png import encode_png
+    rng = np.random.default_rng(1)
+    for shp in ((1, 1, 3), (7, 5, 3), (64, 64, 3), (130, 66, 3), (600, 300, 3), (33, 17, 1)):
+        a = rng.integers(0, 256, shp, dtype=np.uint8)
+        if shp[0] >= 64:
+            a[: shp[0] // 2] = (np.arange(shp[1])[None, :, None] * 3 % 256).astype(np.uint8)      # compressible half
+        for level in (0, 3, 9):
+            im = np.asarray(Image.open(io.BytesIO(encode_png(a, level))))
+            im = im[:, :, None] if shp[2] == 1 else im
+            assert im.shape == a.shape and (im == a).all(), (shp, level)
