@@ -76,6 +76,7 @@ SIGNATURES = {
     "ddpm_ddim_step": [_vp, _vp, _vp, _i, _vp, _vp, _vp, _f, _vp, _f, _i, _vp, _i, _i64, _vp],
     "ddpm_to_image01": [_vp, _vp, _i64, _vp],
     "ddpm_image_grid": [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp],
+    "ddpm_batch_from_u8": [_vp, _i64, _vp, _i, _i, _i, _vp, _vp],
     "ddpm_nchw_to_nhwc": [_vp, _i, _i, _i64, _i64, _i64, _i64, _TP, _i, _vp],
     "ddpm_nhwc_to_nchw": [_TP, _i, _vp, _i, _i64, _i64, _i64, _i64, _vp],
     "ddpm_sinusoid": [_vp, _i, _i, _i, _vp, _i, _vp],

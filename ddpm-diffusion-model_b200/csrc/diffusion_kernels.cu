@@ -487,6 +487,35 @@ extern "C" int ddpm_image_grid(const float* x01, int N, int C, int H, int W, int
     return 0;
 }
 
+// ---------------------------------------------------------------- device-resident batch feeder (input side)
+// ToTensor + Normalize([0.5]*3, [0.5]*3) of the reference's loaders (src/data/load_data_local.py:90-95,
+// celebraHQ.py:40-43) applied to a uint8 NHWC dataset that lives in HBM: out[b][c][y][x] = (u8/255 - 0.5) / 0.5 for the
+// sample idx[b], written as the NCHW fp32 batch `train_one_epoch` expects.  One thread per pixel (3 bytes in, three
+// coalesced plane writes out); 3 B read + 12 B written per pixel.
+__global__ void batch_from_u8_kernel(const uint8_t* __restrict__ data, const int64_t* __restrict__ idx, int B, int64_t hw,
+                                     float* __restrict__ out) {
+    pdl_enter();
+    const int64_t total = (int64_t)B * hw;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int b = (int)(i / hw); const int64_t p = i - (int64_t)b * hw;
+        const uint8_t* src = data + ((int64_t)idx[b] * hw + p) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float t = __fdiv_rn((float)src[c], 255.f);                 // ToTensor
+            out[((int64_t)b * 3 + c) * hw + p] = __fdiv_rn(__fsub_rn(t, 0.5f), 0.5f);   // Normalize(0.5, 0.5)
+        }
+    }
+}
+extern "C" int ddpm_batch_from_u8(const uint8_t* data, int64_t n_images, const int64_t* idx, int B, int H, int W, float* out,
+                                  void* stream) {
+    if (!data || !idx || !out || n_images <= 0 || B <= 0 || H <= 0 || W <= 0) return DDPM_E_ARG;
+    const int64_t hw = (int64_t)H * W, total = (int64_t)B * hw;
+    int grid = (int)((total + 255) / 256); if (grid > 148 * 16) grid = 148 * 16;
+    CUDA_TRY(launch_pdl(batch_from_u8_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, data, idx, B, hw, out));
+    LAUNCH_OK();
+    return 0;
+}
+
 // ---------------------------------------------------------------- layout conversion
 template <typename TS, typename TD, bool TO_NHWC>
 __global__ void layout_kernel(char* nchw, int64_t sn, int64_t sc, int64_t sh, int64_t sw, TV v, int srcC) {

@@ -85,6 +85,12 @@ int ddpm_to_image01(const float* x, float* out, int64_t n, void* stream);
 int ddpm_image_grid(const float* x01, int N, int C, int H, int W, int nrow, int pad, float* grid_f32, uint8_t* grid_u8,
                     void* stream);
 
+/* Input side: one batch of a uint8 NHWC dataset resident in HBM -> fp32 NCHW in [-1,1], i.e.
+ * transforms.ToTensor() + Normalize([0.5]*3,[0.5]*3) of src/data/load_data_local.py:90-95 / celebraHQ.py:40-43 for the
+ * samples idx[0..B) (device int64; out of range is undefined behaviour -- the host side generates the permutation). */
+int ddpm_batch_from_u8(const uint8_t* data, int64_t n_images, const int64_t* idx, int B, int H, int W, float* out,
+                       void* stream);
+
 /* ---------------- layout at the API boundary (NCHW-shaped, any strides <-> NHWC) ---------- */
 /* dst->C may exceed src_C (channel padding for the tensor-core kernels): the extra channels are
  * written as zeros. */

@@ -295,3 +295,20 @@ def test_png_encoder_round_trips_through_pil():
             im = np.asarray(Image.open(io.BytesIO(encode_png(a, level))))
             im = im[:, :, None] if shp[2] == 1 else im
             assert im.shape == a.shape and (im == a).all(), (shp, level)
+
+
+def test_device_loader_epoch_order_matches_torch_dataloader():
+    """Input side: the feeder's permutation is drawn from the generator exactly like
+    DataLoader(shuffle=True, generator=g) does, epoch after epoch."""
+    from torch.utils.data import DataLoader, TensorDataset
+    from ddpm_diffusion_model_b200.data.device_loader import DeviceLoader
+    n = 53
+    ref = DataLoader(TensorDataset(torch.arange(n)), batch_size=8, shuffle=True, generator=torch.Generator().manual_seed(21))
+    g = torch.Generator().manual_seed(21)
+    for _ in range(3):                                          # three complete epochs of the reference loader
+        want = torch.cat([b[0] for b in ref])
+        assert torch.equal(DeviceLoader.epoch_order(n, True, g), want)
+    assert torch.equal(DeviceLoader.epoch_order(7, False, None), torch.arange(7))
+    torch.manual_seed(9); a = DeviceLoader.epoch_order(n, True, None)
+    torch.manual_seed(9); b = torch.cat([t[0] for t in DataLoader(TensorDataset(torch.arange(n)), batch_size=8, shuffle=True)])
+    assert torch.equal(a, b)
