@@ -249,10 +249,12 @@ def train_one_epoch(model, diffusion, dataloader, optimizer, *, scaler=None, ema
                 probe_msg = ""
                 if probe_timesteps:
                     with torch.no_grad(), autocast_ctx(device="cuda", enabled=True, dtype="bf16"):
-                        vals = []
+                        probes = []
                         for tau in probe_timesteps:
                             t_fix = torch.full((B,), int(tau), device=dev, dtype=torch.long)
-                            vals.append(f"t={tau}:{diffusion.loss_simple(model, x, t_fix).item():.3f}")
+                            probes.append(diffusion.loss_simple(model, x, t_fix).detach().float())
+                        # ONE host read for all probes (the reference syncs once per probe, train_one_epoch.py:134-142)
+                        vals = [f"t={tau}:{v:.3f}" for tau, v in zip(probe_timesteps, torch.stack(probes).tolist())]
                         probe_msg = " | " + " ".join(vals)
                 mem_msg = ""
                 if log_mem:
