@@ -566,6 +566,9 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_c
     const int cols_per_buf = MT * p.NT;
 
     if (threadIdx.x == 0) {
+        // descriptor fetch (128 B each from the parameter bank) overlaps barrier set-up / TMEM allocation / cluster sync
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         for (int i = 0; i < p.S; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 16); }
         fence_barrier_init();
@@ -964,6 +967,8 @@ __global__ void __launch_bounds__(TC_THREADS) wgrad_tc_kernel(const __grid_const
     const int y_bytes = 2 * WG_KQ * 128;                 // two 64-channel blocks of dY
 
     if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         // cluster mode: rank 0 multicasts dY into all three CTAs, so ITS empty[s] collects the release of all three
         // MMA warps (the others' commits arrive remotely); ranks 1, 2 only wait for their own
         for (int i = 0; i < WG_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], (p.cl3 && crank == 0) ? 3 : 1); }
