@@ -8,6 +8,7 @@
 // vector position `cv` and walks pixels, so global accesses are 16 B per lane and contiguous along C.
 //
 // HBM roofline (bf16 activations): gn_stats 2 B/elem, gn_apply 4 B/elem, gn_bwd 2x(4)+2 = 10 B/elem.
+#include <stdlib.h>
 #include "common.cuh"
 
 #include <cooperative_groups.h>
@@ -461,10 +462,16 @@ __global__ void __launch_bounds__(NT, STASH ? GN_BWD_OCC : 2) gn_bwd_kernel(GnP 
 }
 
 // cluster size: enough CTAs per image that a thread sees ~16 packets per phase, at most 8 (portable limit)
+static int gn_max_cluster() {              // experiment: DDPM_B200_GN_CS16=1 allows the non-portable cluster size 16
+    static int v = 0;
+    if (v == 0) { const char* e = getenv("DDPM_B200_GN_CS16"); v = (e && e[0] == '1') ? 16 : 8; }
+    return v;
+}
 static int gn_cluster_size(int HW, int cvs) {
     const int64_t packets = (int64_t)HW * cvs;
     int cs = 1;
     while (cs < 8 && packets / (cs * NT) >= 24) cs <<= 1;
+    if (cs == 8 && gn_max_cluster() == 16 && packets / (16 * NT) >= 12) cs = 16;
     return cs;
 }
 static int log2_exact(int v) { int s = 0; while ((1 << s) < v) ++s; return (1 << s) == v ? s : -1; }
@@ -478,6 +485,15 @@ static int launch_cluster(K kernel, int grid, int cs, size_t smem, cudaStream_t 
             cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return (int)e;
             have = smem;
+        }
+    }
+    if (cs > 8) {
+        static std::unordered_map<const void*, int> np;
+        int& have = np[(const void*)kernel];
+        if (!have) {
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            if (e != cudaSuccess) return (int)e;
+            have = 1;
         }
     }
     cudaLaunchConfig_t cfg = {};
