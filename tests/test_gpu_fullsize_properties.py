@@ -77,7 +77,8 @@ def test_groupnorm_invariants_and_backward_adjoint_at_full_batch():
     # scale invariance: GN(4 x) = GN(x) up to eps (4 is exact in bf16)
     x4 = E.act(B, H, H, C); x4.interior().copy_(x.interior().float() * 4.0)
     y4, _ = engine.gn_fwd(E, x4, gn, 0, 0.0, 0)
-    assert float((y4.interior().float() - y.interior().float()).abs().max()) < 2e-2
+    d4 = y4.interior().float() - y.interior().float()
+    assert float(d4.norm() / y.interior().float().norm()) < 2e-3 and float((d4.abs() / (1 + y.interior().float().abs())).max()) < 2 ** -6
     # statistics: the stored sums are the fp64 sums of the bf16 inputs
     xi = x.interior().double().reshape(B, H * H, G, C // G)
     assert torch.allclose(st[:, :, 0], xi.sum((1, 3)), rtol=1e-6, atol=1e-3)
@@ -116,7 +117,7 @@ def test_q_sample_predict_x0_round_trip_at_full_batch():
     assert float((back - x0).abs().max()) < 2e-4
     # variance bookkeeping of the forward process: ab_t * E[x0^2] + (1 - ab_t) per sample
     ab = d.alphas_cumprod[t].double()
-    want = ab * (x0.double() ** 2).mean((1, 2, 3)) + (1 - ab) * (eps.double() ** 2).mean((1, 2, 3)) \\
+    want = ab * (x0.double() ** 2).mean((1, 2, 3)) + (1 - ab) * (eps.double() ** 2).mean((1, 2, 3)) \
         + 2 * (ab * (1 - ab)).sqrt() * (x0.double() * eps.double()).mean((1, 2, 3))
     assert torch.allclose((xt.double() ** 2).mean((1, 2, 3)), want, rtol=1e-5)
 
