@@ -231,6 +231,7 @@ __global__ void __launch_bounds__(NT, GN_FWD_OCC) gn_fwd_kernel(GnP a) {
     extern __shared__ __align__(16) unsigned char gsm[];
     pdl_enter();
     const int C = a.x.C, G = a.G, cpg = C / G, HW = a.x.H * a.x.W;
+    constexpr bool FAST_ACT = sizeof(T) == 2;                // bf16 tensors: tanh-based SiLU (common.cuh)
     constexpr int RING = gn_ring_bytes<VEC, 1>();
     unsigned char* ring = gsm;
     float (*part)[NT] = reinterpret_cast<float (*)[NT]>(gsm);    // aliases the ring (see gn_ring_bytes)
@@ -302,6 +303,7 @@ __global__ void __launch_bounds__(NT, GN_FWD_OCC) gn_fwd_kernel(GnP a) {
             const int c = c0 + i, g = c / cpg;
             sc[i] = gr[g] * __ldg(a.gamma + c);
             sh[i] = __ldg(a.beta + c) - gm[g] * sc[i];
+            if (FAST_ACT && a.act) { sc[i] *= 0.5f; sh[i] *= 0.5f; }     // the affine produces z/2 directly (silu_half)
         }
         stream_packets<T, VEC, 1>(ring, 1, p0 + m.prow, p1, m.ppi, xaddr, [&](int p, Raw<T, VEC>* r) {
             float v[VEC];
@@ -309,7 +311,7 @@ __global__ void __launch_bounds__(NT, GN_FWD_OCC) gn_fwd_kernel(GnP a) {
 #pragma unroll
             for (int i = 0; i < VEC; ++i) {
                 const float z = fmaf(v[i], sc[i], sh[i]);
-                v[i] = a.act ? silu_f(z) : z;
+                v[i] = a.act ? (FAST_ACT ? silu_half(z) : silu_f(z)) : z;
             }
             if (a.thr16) dropout_apply<VEC>(v, dkey, ebase + (uint32_t)p * (uint32_t)C, a.thr16, a.keep_scale);
             stv<T, VEC>(ao.at(ob, p), v);
@@ -326,6 +328,7 @@ __global__ void __launch_bounds__(NT, STASH ? GN_BWD_OCC : 2) gn_bwd_kernel(GnP 
     extern __shared__ __align__(16) unsigned char gsm[];
     pdl_enter();
     const int C = a.x.C, G = a.G, cpg = C / G, HW = a.x.H * a.x.W;
+    constexpr bool FAST_ACT = sizeof(T) == 2;                // bf16 tensors: tanh-based SiLU (common.cuh)
     constexpr int RING = gn_ring_bytes<VEC, 3>();
     unsigned char* ring = gsm;
     float (*part)[NT] = reinterpret_cast<float (*)[NT]>(gsm);    // aliases the ring (see gn_ring_bytes)
@@ -368,6 +371,7 @@ __global__ void __launch_bounds__(NT, STASH ? GN_BWD_OCC : 2) gn_bwd_kernel(GnP 
         for (int i = 0; i < VEC; ++i) {
             const int c = min(c0 + i, C - 1), g = c / cpg;
             sc[i] = gr[g] * __ldg(a.gamma + c); sh[i] = __ldg(a.beta + c) - gm[g] * sc[i];
+            if (FAST_ACT) { sc[i] *= 0.5f; sh[i] *= 0.5f; }          // z/2 for dsilu_half (z itself is only needed there)
         }
         float acc[2 * VEC];
 #pragma unroll
@@ -379,7 +383,7 @@ __global__ void __launch_bounds__(NT, STASH ? GN_BWD_OCC : 2) gn_bwd_kernel(GnP 
 #pragma unroll
             for (int i = 0; i < VEC; ++i) {
                 float dz = d[i];
-                if (a.act) dz *= dsilu_f(fmaf(v[i], sc[i], sh[i]));
+                if (a.act) dz *= FAST_ACT ? dsilu_half(fmaf(v[i], sc[i], sh[i])) : dsilu_f(fmaf(v[i], sc[i], sh[i]));
                 acc[i] += dz; acc[VEC + i] = fmaf(dz, v[i], acc[VEC + i]);
                 d[i] = dz;
             }
@@ -435,7 +439,10 @@ __global__ void __launch_bounds__(NT, STASH ? GN_BWD_OCC : 2) gn_bwd_kernel(GnP 
                 if (a.thr16) dropout_apply<VEC>(d, dkey, ebase + (uint32_t)p * (uint32_t)C, a.thr16, a.keep_scale);
                 if (a.act) {
 #pragma unroll
-                    for (int i = 0; i < VEC; ++i) d[i] *= dsilu_f(fmaf(fmaf(v[i], rs[i], -mr[i]), ga[i], be[i]));
+                    for (int i = 0; i < VEC; ++i) {
+                        const float z = fmaf(fmaf(v[i], rs[i], -mr[i]), ga[i], be[i]);
+                        d[i] *= FAST_ACT ? dsilu_half(0.5f * z) : dsilu_f(z);
+                    }
                 }
             }
 #pragma unroll
