@@ -53,6 +53,8 @@ class ParamArena:
             zero = False
         elif zero:
             self.grad.zero_()
+        if self.grads_attached() and all(p.grad is not None for p in self.params):
+            return self.grad                                 # views are still in place: nothing to rebuild (0.5 ms per call)
         gv = self.views(self.grad)
         for p, g in zip(self.params, gv):
             if p.requires_grad:

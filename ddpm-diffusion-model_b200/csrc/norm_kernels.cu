@@ -95,8 +95,11 @@ static inline int blocks_per_image(int N, int HW, int ppi) {
 // no registers are held by loads in flight, no barriers (a thread only reads what it copied itself; completion
 // through cp.async.wait_group), and 1024 threads x 3 iterations x 16-48 B stay in flight per SM.
 #ifndef GN_PIPE_D
-#define GN_PIPE_D 4               // power of two
+#define GN_PIPE_D 4               // backward (2-3 tensors per iteration); power of two
 #endif
+#ifndef GN_PIPE_D_FWD
+#define GN_PIPE_D_FWD 8           // forward streams ONE tensor: 3 x 16 B per thread was only ~48 KB in flight per SM, at the
+#endif                            // latency x bandwidth threshold (43 KB) -- the statistics pass ran at 3.4 TB/s
 __device__ __forceinline__ uint32_t sm_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -108,13 +111,13 @@ __device__ __forceinline__ uint4 lds128(uint32_t a) {
     asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
     return v;
 }
-template <int VEC, int NTEN> constexpr int gn_ring_bytes() {
+template <int VEC, int NTEN, int D = GN_PIPE_D> constexpr int gn_ring_bytes() {
     // the ring doubles as the [2*VEC][NT] float scratch of cta_channel_reduce (used only between streaming loops)
-    return VEC == 1 ? 2 * NT * 4 : (GN_PIPE_D * NTEN * NT * 16 > 2 * VEC * NT * 4 ? GN_PIPE_D * NTEN * NT * 16 : 2 * VEC * NT * 4);
+    return VEC == 1 ? 2 * NT * 4 : (D * NTEN * NT * 16 > 2 * VEC * NT * 4 ? D * NTEN * NT * 16 : 2 * VEC * NT * 4);
 }
 // Calls body(p, r) for p = first, first+step, ... < end with r[t] = the 16-byte packet of tensor t (t < nten <= NTEN)
 // at pixel p, addr(t, p) giving its global address.  VEC == 1 (unaligned fallbacks) loads directly.
-template <typename T, int VEC, int NTEN, typename AddrF, typename BodyF>
+template <typename T, int VEC, int NTEN, int D = GN_PIPE_D, typename AddrF, typename BodyF>
 __device__ __forceinline__ void stream_packets(unsigned char* ring, int nten, int first, int end, int step, AddrF addr, BodyF body) {
     if constexpr (VEC == 1) {
         for (int p = first; p < end; p += step) {
@@ -124,7 +127,6 @@ __device__ __forceinline__ void stream_packets(unsigned char* ring, int nten, in
             body(p, r);
         }
     } else {
-        constexpr int D = GN_PIPE_D;
         const uint32_t base = sm_u32(ring) + threadIdx.x * 16u;
         int pi = first;
 #pragma unroll
@@ -232,7 +234,7 @@ __global__ void __launch_bounds__(NT, GN_FWD_OCC) gn_fwd_kernel(GnP a) {
     pdl_enter();
     const int C = a.x.C, G = a.G, cpg = C / G, HW = a.x.H * a.x.W;
     constexpr bool FAST_ACT = sizeof(T) == 2;                // bf16 tensors: tanh-based SiLU (common.cuh)
-    constexpr int RING = gn_ring_bytes<VEC, 1>();
+    constexpr int RING = gn_ring_bytes<VEC, 1, GN_PIPE_D_FWD>();
     unsigned char* ring = gsm;
     float (*part)[NT] = reinterpret_cast<float (*)[NT]>(gsm);    // aliases the ring (see gn_ring_bytes)
     double* chan = reinterpret_cast<double*>(gsm + RING);     // [2][C]
@@ -258,7 +260,7 @@ __global__ void __launch_bounds__(NT, GN_FWD_OCC) gn_fwd_kernel(GnP a) {
         float acc[2 * VEC];
 #pragma unroll
         for (int i = 0; i < 2 * VEC; ++i) acc[i] = 0.f;
-        stream_packets<T, VEC, 1>(ring, 1, p0 + m.prow, pend, m.ppi, xaddr, [&](int, Raw<T, VEC>* r) {
+        stream_packets<T, VEC, 1, GN_PIPE_D_FWD>(ring, 1, p0 + m.prow, pend, m.ppi, xaddr, [&](int, Raw<T, VEC>* r) {
             float v[VEC];
             unraw<T, VEC>(r[0], v);
 #pragma unroll
@@ -305,7 +307,7 @@ __global__ void __launch_bounds__(NT, GN_FWD_OCC) gn_fwd_kernel(GnP a) {
             sh[i] = __ldg(a.beta + c) - gm[g] * sc[i];
             if (FAST_ACT && a.act) { sc[i] *= 0.5f; sh[i] *= 0.5f; }     // the affine produces z/2 directly (silu_half)
         }
-        stream_packets<T, VEC, 1>(ring, 1, p0 + m.prow, p1, m.ppi, xaddr, [&](int p, Raw<T, VEC>* r) {
+        stream_packets<T, VEC, 1, GN_PIPE_D_FWD>(ring, 1, p0 + m.prow, p1, m.ppi, xaddr, [&](int p, Raw<T, VEC>* r) {
             float v[VEC];
             unraw<T, VEC>(r[0], v);
 #pragma unroll
@@ -535,7 +537,7 @@ static int gn_fwd_dispatch(GnP& p, const ddpm_tensor* x, const ddpm_tensor* out,
 #define GO(T, VEC) { int cvs = C / VEC; if (cvs > NT) return DDPM_E_ARG; \
         int cs = MODE == 2 ? 1 : gn_cluster_size(HW, cvs); \
         if (MODE == 2) { cs = 1; int want = (HW * cvs) / (NT * 16); while (cs < 8 && cs < want) cs <<= 1; } \
-        return launch_cluster(gn_fwd_kernel<T, VEC, MODE>, x->N * cs, cs, sm0 + gn_ring_bytes<VEC, 1>(), st, p); }
+        return launch_cluster(gn_fwd_kernel<T, VEC, MODE>, x->N * cs, cs, sm0 + gn_ring_bytes<VEC, 1, GN_PIPE_D_FWD>(), st, p); }
     const bool v8 = vec_ok(x, 8, 2) && (MODE == 1 || vec_ok(out, 8, 2));
     const bool v4 = vec_ok(x, 4, 4) && (MODE == 1 || vec_ok(out, 4, 4));
     if (dtype == DDPM_BF16) { if (v8) GO(bf16, 8) else GO(bf16, 1) }
