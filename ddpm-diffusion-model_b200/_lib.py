@@ -28,7 +28,7 @@ class ConvArgs(C.Structure):
                 ("tbias", C.c_void_p), ("tbias_pitch", C.c_int32), ("res", Tensor), ("z", Tensor),
                 ("KH", C.c_int32), ("KW", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32),
                 ("mode", C.c_int32), ("a_silu", C.c_int32), ("epi", C.c_int32), ("dtype", C.c_int32),
-                ("prefer_tc", C.c_int32), ("bias_n", C.c_int32)]
+                ("prefer_tc", C.c_int32), ("bias_n", C.c_int32), ("in2", Tensor), ("w2", C.c_void_p)]
 
 
 class WgradArgs(C.Structure):

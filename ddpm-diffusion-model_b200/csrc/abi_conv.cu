@@ -27,6 +27,19 @@ extern "C" int ddpm_conv(const ddpm_conv_args* a, void* stream) {
     if (a->res.ptr && (!tensor_ok(&a->res) || a->res.C != a->out.C || a->res.H != a->out.H || a->res.W != a->out.W)) return DDPM_E_ARG;
     if (a->z.ptr && (!tensor_ok(&a->z) || a->z.C != a->out.C || a->z.H != a->out.H || a->z.W != a->out.W)) return DDPM_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
+    if (a->in2.ptr) {
+        if (!tensor_ok(&a->in2) || !a->w2 || a->mode != DDPM_CONV_NORMAL || a->stride != 1 || a->a_silu) return DDPM_E_ARG;
+        if (a->in2.N != a->out.N || a->in2.H != a->out.H || a->in2.W != a->out.W) return DDPM_E_ARG;
+        if (a->prefer_tc && !g_force_simt && conv_tc_supported(a)) return conv_tc_launch(a, st);      // one launch, K = 9*Cin + Cin2
+        // every other path: the same sum as two launches (the 1x1 accumulates into the main result)
+        ddpm_conv_args m = *a; m.in2.ptr = nullptr; m.w2 = nullptr;
+        int rc = ddpm_conv(&m, stream); if (rc) return rc;
+        ddpm_conv_args s2 = *a;
+        s2.in = a->in2; s2.w = a->w2; s2.in2.ptr = nullptr; s2.w2 = nullptr;
+        s2.KH = s2.KW = 1; s2.pad = 0; s2.bias = nullptr; s2.bias_n = 0; s2.tbias = nullptr; s2.res.ptr = nullptr; s2.z.ptr = nullptr;
+        s2.epi = DDPM_EPI_ACCUM;
+        return ddpm_conv(&s2, stream);
+    }
     if (a->prefer_tc && !g_force_simt && conv_tc_supported(a)) return conv_tc_launch(a, st);
     return conv_simt_launch(a, st);
 }

@@ -357,6 +357,7 @@ static int pick_nt(int Cout) {
     return 0;
 }
 
+int g_tc_v2_flag();
 int conv_tc_supported(const ddpm_conv_args* a) {
     if (a->dtype != DDPM_BF16 || a->mode != DDPM_CONV_NORMAL || a->a_silu || a->z.ptr) return 0;
     if (!((a->KH == 3 && a->KW == 3 && a->pad == 1) || (a->KH == 1 && a->KW == 1 && a->pad == 0))) return 0;
@@ -370,6 +371,11 @@ int conv_tc_supported(const ddpm_conv_args* a) {
     if (a->res.ptr && (a->res.halo != 1 || a->res.pitch % 8 || ((uintptr_t)a->res.ptr & 15))) return 0;
     if (pick_nt(out.C) == 0) return 0;
     if (in.W + 2 > 300) return 0;         // patch would not fit the A ring (large images: later round)
+    if (a->in2.ptr) {                     // fused 1x1 second operand: persistent pair kernel, 3x3 stride-1 main conv only
+        const ddpm_tensor& i2 = a->in2;
+        if (!g_tc_v2_flag() || g_tc_mode != 1 || a->KH != 3 || a->stride != 1 || (a->epi & DDPM_EPI_DSILU)) return 0;
+        if (i2.halo != 1 || i2.C % 16 || i2.pitch % 8 || ((uintptr_t)i2.ptr & 15) || ((uintptr_t)a->w2 & 15)) return 0;
+    }
     return 1;
 }
 
@@ -541,16 +547,21 @@ struct Tc2Params {
     int v256;                     // out (and res) rows are 32-byte aligned -> 256-bit loads / stores
     int b_res;                    // 1: this CTA's half of the weight tile (all K-chunks, all taps) stays resident in shared
                                   //    memory -- loaded once, with the first item's stages -- and only A patches stream
+    int KCH2;                     // K-chunks of the fused 1x1 second operand (0: none): they follow the 3x3 chunks of every
+    int b2_chunk_bytes;           //    item, load their patch through tmA2 / their one-tap weight slab through tmB2 and
+                                  //    issue only the centre tap
 };
 
 template <int MT, int TAPS>
 __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                                    const __grid_constant__ CUtensorMap tmB, Tc2Params p) {
+                                                                    const __grid_constant__ CUtensorMap tmB,
+                                                                    const __grid_constant__ CUtensorMap tmA2,
+                                                                    const __grid_constant__ CUtensorMap tmB2, Tc2Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* ring = smem;
     uint8_t* bres = ring + (size_t)p.S * p.stage_bytes;                                   // resident weights (b_res only)
-    uint64_t* bars = (uint64_t*)(bres + (p.b_res ? (size_t)(p.Cin / KC) * p.b_chunk_bytes : 0));
+    uint64_t* bars = (uint64_t*)(bres + (p.b_res ? (size_t)(p.Cin / KC) * p.b_chunk_bytes + (size_t)p.KCH2 * p.b2_chunk_bytes : 0));
     uint64_t* full = bars;            uint64_t* empty = full + p.S;
     uint64_t* tfull = empty + p.S;    uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
@@ -560,7 +571,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_c
     const bool leader = rank == 0;
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
     const int KCH = p.Cin / KC;
-    const int NST = (KCH + p.KS - 1) / p.KS;            // ring stages per item
+    const int NST = (KCH + p.KS - 1) / p.KS + p.KCH2;   // ring stages per item (KS = 1 whenever a second operand is fused)
     const int halo_rows = (p.taps == 9) ? p.Wp + 1 : 0;
     const int tile_rows = 128 * MT;
     const int cols_per_buf = MT * p.NT;
@@ -569,6 +580,10 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_c
         // descriptor fetch (128 B each from the parameter bank) overlaps barrier set-up / TMEM allocation / cluster sync
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        if (p.KCH2) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA2) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB2) : "memory");
+        }
         for (int i = 0; i < p.S; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 16); }
         fence_barrier_init();
@@ -592,20 +607,26 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_c
                 for (int st = 0; st < NST; ++st, ++g) {
                     const int s = g % p.S; const uint32_t ph = (g / p.S) & 1;
                     mbar_wait(&empty[s], ph ^ 1);
-                    const int kc0 = st * p.KS, nk = min(p.KS, KCH - kc0);
+                    const bool second = st >= NST - p.KCH2;                       // a chunk of the fused 1x1 operand
+                    const int kc0 = second ? st - (NST - p.KCH2) : st * p.KS, nk = second ? 1 : min(p.KS, KCH - kc0);
                     const uint32_t fbar = mapa_u32(smem_u32(&full[s]), 0);
                     const bool skipA = (p.exp & 1) && g >= (uint32_t)p.S, skipB = (p.exp & 2) && g >= (uint32_t)p.S;   // diagnostics
                     const bool loadB = !skipB && !(p.b_res && it != pair);       // resident weights arrive with the first item only
-                    const uint32_t tx = (uint32_t)(2 * nk * ((skipA ? 0 : p.P * 32) + (loadB ? p.b_chunk_bytes : 0)));
+                    const int bbytes = second ? p.b2_chunk_bytes : p.b_chunk_bytes;
+                    const uint32_t tx = (uint32_t)(2 * nk * ((skipA ? 0 : p.P * 32) + (loadB ? bbytes : 0)));
                     if (leader) { if (tx) mbar_expect_tx(&full[s], tx); else mbar_arrive(&full[s]); }
                     uint8_t* sbase = ring + (size_t)s * p.stage_bytes;
+                    const CUtensorMap* mA = second ? &tmA2 : &tmA;
+                    const CUtensorMap* mB = second ? &tmB2 : &tmB;
                     for (int k = 0; k < nk; ++k) {
                         uint8_t* adst = sbase + (size_t)k * (p.a_chunk_bytes + (p.b_res ? 0 : p.b_chunk_bytes));
-                        uint8_t* bdst = p.b_res ? bres + (size_t)(kc0 + k) * p.b_chunk_bytes : adst + p.a_chunk_bytes;
+                        uint8_t* bdst = !p.b_res ? adst + p.a_chunk_bytes
+                                      : (second ? bres + (size_t)KCH * p.b_chunk_bytes + (size_t)kc0 * p.b2_chunk_bytes
+                                                : bres + (size_t)(kc0 + k) * p.b_chunk_bytes);
                         const int row0 = Q0 - halo_rows;
                         for (int r = 0; r < p.P && !skipA; r += p.seg)
-                            tma2_load_2d(adst + (size_t)r * 32, &tmA, fbar, (kc0 + k) * KC, row0 + r);
-                        if (loadB) tma2_load_3d(bdst, &tmB, fbar, (kc0 + k) * KC, nrow0, 0);
+                            tma2_load_2d(adst + (size_t)r * 32, mA, fbar, (kc0 + k) * KC, row0 + r);
+                        if (loadB) tma2_load_3d(bdst, mB, fbar, (kc0 + k) * KC, nrow0, 0);
                     }
                 }
             }
@@ -636,8 +657,22 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_c
                     const uint32_t s = g % (uint32_t)p.S; const uint32_t ph = (g / (uint32_t)p.S) & 1;
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
-                    const int nk = min(p.KS, KCH - st * p.KS);
                     uint32_t a_lo = ring_lo + s * stage16;
+                    if (st >= NST - p.KCH2) {
+                        // fused 1x1 operand: one MMA per M-tile, the patch's centre tap against the one-tap weight slab
+                        const uint32_t kc2 = (uint32_t)(st - (NST - p.KCH2));
+                        const uint32_t b_lo = p.b_res ? bres_lo + (uint32_t)KCH * bchunk16 + kc2 * (uint32_t)(p.b2_chunk_bytes >> 4) : a_lo + a16;
+                        const uint64_t bdesc = desc_pack(b_lo, hi);
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt) {
+                            const uint64_t adesc = desc_pack(a_lo + tapoff[TAPS / 2] + (uint32_t)(mt * 256), hi);
+                            if (el) umma2_bf16(dbase + (uint32_t)(mt * p.NT), adesc, bdesc, idesc, 1u);
+                        }
+                        if (el) umma2_commit_mc(&empty[s]);
+                        __syncwarp();
+                        continue;
+                    }
+                    const int nk = min(p.KS, KCH - st * p.KS);
                     for (int k = 0; k < nk; ++k, a_lo += chunk16) {
                         const uint32_t b_lo = p.b_res ? bres_lo + (uint32_t)(st * p.KS + k) * bchunk16 : a_lo + a16;
 #pragma unroll
@@ -844,6 +879,8 @@ static int conv_tc2_launch(const ddpm_conv_args* a, cudaStream_t st) {
     p.b_chunk_bytes = p.taps * (p.NT / 2) * 32;             // multiple of 256: NT/2 is a multiple of 8
     const int KCH = p.Cin / KC;
     p.KS = p.taps == 9 ? 1 : (KCH < 4 ? KCH : 4);
+    p.KCH2 = a->in2.ptr ? a->in2.C / KC : 0;                // fused 1x1 second operand (3x3 main conv only: KS == 1)
+    p.b2_chunk_bytes = (p.NT / 2) * 32;
     const int budget = 212 * 1024;
     p.pix_tiles = ceil_div(p.Qtot, 256 * MT);
     p.items = p.pix_tiles * p.n_tiles;
@@ -852,21 +889,32 @@ static int conv_tc2_launch(const ddpm_conv_args* a, cudaStream_t st) {
     // A ring and every CTA pair sees several items: then only activations stream (14.8 instead of 30.8 B/clk/SM at NT=96).
     p.b_res = 0;
     if (p.taps == 9 && !(g_tc_exp & 64)) {
-        const int bres_bytes = KCH * p.b_chunk_bytes;
+        const int bres_bytes = KCH * p.b_chunk_bytes + p.KCH2 * p.b2_chunk_bytes;
         const int pr = pairs - pairs % p.n_tiles;             // a pair keeps ONE channel tile: pairs must be a multiple of n_tiles
         if (bres_bytes + 3 * p.a_chunk_bytes <= budget && pr >= p.n_tiles && p.items >= 3 * pr) { p.b_res = 1; pairs = pr; }
     }
     if (p.b_res) {
         p.stage_bytes = p.a_chunk_bytes;
-        p.S = (budget - KCH * p.b_chunk_bytes) / p.stage_bytes; if (p.S > 12) p.S = 12;
+        p.S = (budget - KCH * p.b_chunk_bytes - p.KCH2 * p.b2_chunk_bytes) / p.stage_bytes; if (p.S > 12) p.S = 12;
     } else {
         p.stage_bytes = (p.KS * (p.a_chunk_bytes + p.b_chunk_bytes) + 1023) & ~1023;
         p.S = budget / p.stage_bytes; if (p.S > 12) p.S = 12;
     }
     if (p.S < 2) return DDPM_E_ARG;
-    size_t smem = (size_t)p.S * p.stage_bytes + (p.b_res ? (size_t)KCH * p.b_chunk_bytes : 0) + 8 * (2 * p.S + 4) + 16 + 1024;
+    size_t smem = (size_t)p.S * p.stage_bytes + (p.b_res ? (size_t)KCH * p.b_chunk_bytes + (size_t)p.KCH2 * p.b2_chunk_bytes : 0) +
+                  8 * (2 * p.S + 4) + 16 + 1024;
 
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmA2, tmB2;
+    if (p.KCH2) {
+        uint64_t da[2] = {(uint64_t)a->in2.C, (uint64_t)p.Qtot}; uint64_t sa[1] = {(uint64_t)a->in2.pitch * 2};
+        uint32_t ba[2] = {KC, (uint32_t)p.seg};
+        if (encode(&tmA2, a->in2.ptr, 2, da, sa, ba, CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
+        // 1x1 weights [Cout][1][Cin2] viewed as (c, n, tap = 1)
+        uint64_t db[3] = {(uint64_t)a->in2.C, (uint64_t)p.Cout, 1};
+        uint64_t sb[2] = {(uint64_t)a->in2.C * 2, (uint64_t)p.Cout * a->in2.C * 2};
+        uint32_t bb[3] = {KC, (uint32_t)(p.NT / 2), 1};
+        if (encode(&tmB2, (void*)a->w2, 3, db, sb, bb, CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
+    }
     {
         uint64_t da[2] = {(uint64_t)p.Cin, (uint64_t)p.Qtot}; uint64_t sa[1] = {(uint64_t)a->in.pitch * 2};
         uint32_t ba[2] = {KC, (uint32_t)p.seg};
@@ -887,7 +935,7 @@ static int conv_tc2_launch(const ddpm_conv_args* a, cudaStream_t st) {
     static size_t configured[4] = {0, 0, 0, 0};
 #define TC2_GO(MTV, TAPSV, SLOT) { \
         if (smem > configured[SLOT]) { CUDA_TRY(cudaFuncSetAttribute(conv_tc2_kernel<MTV, TAPSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured[SLOT] = smem; } \
-        CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<MTV, TAPSV>, tmA, tmB, p)); }
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<MTV, TAPSV>, tmA, tmB, p.KCH2 ? tmA2 : tmA, p.KCH2 ? tmB2 : tmB, p)); }
     if (MT == 2) { if (p.taps == 9) TC2_GO(2, 9, 0) else TC2_GO(2, 1, 1) }
     else { if (p.taps == 9) TC2_GO(1, 9, 2) else TC2_GO(1, 1, 3) }
 #undef TC2_GO

@@ -238,6 +238,11 @@ class Exec:
 _SIDE_STREAMS: Dict[str, "torch.cuda.Stream"] = {}
 
 
+def fuse_skip_enabled() -> bool:
+    import os
+    return os.environ.get("DDPM_B200_FUSE_SKIP", "1") != "0"
+
+
 def overlap_enabled() -> bool:
     import os
     return os.environ.get("DDPM_B200_WGRAD_OVERLAP", "1") != "0"
@@ -291,11 +296,16 @@ def _gptr(p) -> Optional[int]:
 def conv(E: Exec, x: Act, wpack: torch.Tensor, out: Act, k: int, stride: int = 1, pad: int = 0, *,
          bias: Optional[torch.Tensor] = None, tbias: Optional[torch.Tensor] = None, res: Optional[Act] = None,
          z: Optional[Act] = None, accum: bool = False, a_silu: bool = False, mode: int = _lib.CONV_NORMAL,
-         dt: Optional[int] = None) -> Act:
+         dt: Optional[int] = None, in2: Optional[Act] = None, w2pack: Optional[torch.Tensor] = None) -> Act:
+    """`in2` / `w2pack`: out = conv(x; w) + conv1x1(in2; w2) in one launch (see ddpm_conv_args.in2)."""
     dt = x.dt if dt is None else dt
     a = _lib.ConvArgs()
     a.inp, a.out = x.desc(), out.desc()
     a.w = wpack.data_ptr()
+    if in2 is not None:
+        a.in2, a.w2 = in2.desc(), w2pack.data_ptr()
+    else:
+        a.in2, a.w2 = _NULL, None
     a.bias = bias.data_ptr() if bias is not None else None
     a.bias_n = bias.numel() if bias is not None else 0
     if tbias is not None:
@@ -502,8 +512,13 @@ def resblock_fwd(E: Exec, blk, x: Act, tbias: torch.Tensor, out: Optional[Act] =
         out = E.act(x.N, x.H, x.W, Cout)
     if isinstance(blk.skip, torch.nn.Conv2d):
         ws, _ = E.wcache.get(E, blk.skip.weight, E.dt, E.need_grad)
-        conv(E, x, ws, out, 1, bias=blk.skip.bias)
-        conv(E, a2, w2, out, 3, 1, 1, bias=blk.conv2.bias, accum=True)
+        if fuse_skip_enabled() and blk.skip.bias is not None and blk.conv2.bias is not None:
+            # conv2(a2) + skip(x) as ONE implicit GEMM (K = 9*Cout + Cin): no separate 1x1 launch, no read-modify-write of
+            # `out`; the two biases are summed first (a 96..192-element add)
+            conv(E, a2, w2, out, 3, 1, 1, bias=blk.conv2.bias.detach() + blk.skip.bias.detach(), in2=x, w2pack=ws)
+        else:
+            conv(E, x, ws, out, 1, bias=blk.skip.bias)
+            conv(E, a2, w2, out, 3, 1, 1, bias=blk.conv2.bias, accum=True)
     else:
         conv(E, a2, w2, out, 3, 1, 1, bias=blk.conv2.bias, res=x)
     saved = (x, st1, a1, h, st2, a2, p_drop, layer) if E.need_grad else None

@@ -169,6 +169,11 @@ typedef struct {
     int32_t dtype;
     int32_t prefer_tc;     /* 1: use the tcgen05 kernel when the shape qualifies (bf16 only) */
     int32_t bias_n;        /* entries in `bias` (0: out.C); fewer when out carries zero-padded channels */
+    /* Optional second operand: out = conv(in; w) + conv1x1(in2; w2) (+ bias ...), i.e. the ResBlock's `conv2(h) + skip(x)`
+     * (unet_backbone.py:35,46) as ONE implicit GEMM whose K dimension is 9*Cin + Cin2.  in2 has the geometry of `out`
+     * (stride-1 main conv); w2 is packed [Cout][1][Cin2].  in2.ptr == NULL: none. */
+    ddpm_tensor in2;
+    const void* w2;
 } ddpm_conv_args;
 int ddpm_conv(const ddpm_conv_args* a, void* stream);
 /* test / tuning hooks: force the CUDA-core kernels; choose the tcgen05 operand layout

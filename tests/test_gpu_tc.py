@@ -59,6 +59,44 @@ def test_conv_tc_matches_simt(mods, case):
         assert float(full[:, 0].abs().max() + full[:, -1].abs().max() + full[:, :, 0].abs().max() + full[:, :, -1].abs().max()) == 0
 
 
+FUSED = [  # N, Cmain, Cin2, Cout, H  -- out = conv3x3(a; w) + conv1x1(x2; w2) + bias, the ResBlock's conv2 + skip
+    (2, 96, 288, 96, 64), (2, 192, 384, 192, 32), (3, 192, 96, 192, 32), (4, 192, 384, 192, 16), (8, 192, 384, 192, 8),
+    (2, 96, 192, 96, 64), (1, 32, 16, 32, 16), (40, 96, 288, 96, 64),
+]
+
+
+@pytest.mark.parametrize("case", FUSED)
+def test_conv_with_fused_1x1_second_operand(mods, case):
+    """One launch (K = 9*Cmain + Cin2 on the tensor cores) against the two-launch form on the CUDA cores; the second
+    operand is a channel slice of a wider buffer, like the concatenated up-path input."""
+    _lib, engine = mods
+    N, Cm, C2, Co, H = case
+    torch.manual_seed(4)
+    E = engine.Exec(dev(), _lib.BF16, False, False)
+    w = torch.nn.Parameter(torch.randn(Co, Cm, 3, 3, device=dev()) / (Cm * 9) ** 0.5)
+    w2 = torch.nn.Parameter(torch.randn(Co, C2, 1, 1, device=dev()) / C2 ** 0.5)
+    b = torch.randn(Co, device=dev())
+    wf, _ = E.wcache.get(E, w, _lib.BF16, False)
+    w2f, _ = E.wcache.get(E, w2, _lib.BF16, False)
+    a = E.act(N, H, H, Cm); a.interior().normal_()
+    wide = E.act(N, H, H, C2 + 32); wide.interior().normal_()
+    x2 = wide.slice(16, C2)
+    y_ref, y_tc = E.act(N, H, H, Co), E.act(N, H, H, Co)
+    _lib.lib.ddpm_set_force_simt(1)
+    engine.conv(E, a, wf, y_ref, 3, 1, 1, bias=b, in2=x2, w2pack=w2f)
+    _lib.lib.ddpm_set_force_simt(0)
+    n0 = _lib.launch_count(reset=True)
+    engine.conv(E, a, wf, y_tc, 3, 1, 1, bias=b, in2=x2, w2pack=w2f)
+    torch.cuda.synchronize()
+    assert _lib.launch_count(reset=True) == 1                         # really one kernel
+    assert relerr(y_tc.buf.t, y_ref.buf.t) < 1e-2
+    ref = torch.nn.functional.conv2d(a.interior().float().permute(0, 3, 1, 2), w.detach().bfloat16().float(), b, padding=1) + \
+        torch.nn.functional.conv2d(x2.interior().float().permute(0, 3, 1, 2), w2.detach().bfloat16().float())
+    assert relerr(y_tc.interior().float().permute(0, 3, 1, 2), ref) < 1e-2
+    full = y_tc.buf.t.float()
+    assert float(full[:, 0].abs().max() + full[:, -1].abs().max() + full[:, :, 0].abs().max() + full[:, :, -1].abs().max()) == 0
+
+
 WGRAD = [  # N, Cin, Cout, H, W, k
     (2, 32, 32, 16, 16, 3), (2, 96, 96, 64, 64, 3), (4, 192, 192, 32, 32, 3), (2, 288, 96, 64, 64, 3),
     (2, 384, 192, 16, 16, 3), (8, 192, 192, 8, 8, 3), (2, 96, 192, 32, 32, 3), (1, 512, 512, 16, 16, 3),
