@@ -48,7 +48,7 @@ class PackEntry(C.Structure):
 
 class LinEntry(C.Structure):
     """struct ddpm_lin_entry"""
-    _fields_ = [("w", C.c_void_p), ("bias", C.c_void_p), ("N", C.c_int32), ("col0", C.c_int32)]
+    _fields_ = [("w", C.c_void_p), ("bias", C.c_void_p), ("N", C.c_int32), ("col0", C.c_int32), ("bias2", C.c_void_p)]
 
 
 class AdamHyper(C.Structure):

@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(256) linear_grouped_fwd_kernel(const float* __
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const int m = m0 + ty * 2 + i, n = n0 + tx * 2 + j;
-            if (m < M && n < e.N) out[(int64_t)m * opitch + e.col0 + n] = acc[i][j] + (e.bias ? e.bias[n] : 0.f);
+            if (m < M && n < e.N) out[(int64_t)m * opitch + e.col0 + n] = acc[i][j] + (e.bias ? e.bias[n] : 0.f) + (e.bias2 ? e.bias2[n] : 0.f);
         }
 }
 

@@ -193,6 +193,8 @@ typedef struct {
     const float* w;      /* fp32 [N][K] (the nn.Linear weight itself) */
     const float* bias;   /* fp32 [N] or NULL */
     int32_t N, col0;     /* output features; first output column in `out` */
+    const float* bias2;  /* optional second fp32 [N] bias added as well: the bias of the convolution that consumes this
+                          * time bias (unet_backbone.py:40-41), so that its epilogue adds ONE per-image vector */
 } ddpm_lin_entry;
 int ddpm_linear_grouped_fwd(const float* x, int M, int K, int xpitch, const ddpm_lin_entry* entries_dev, int n,
                             int max_N, float* out, int out_pitch, int a_silu, void* stream);

@@ -68,3 +68,10 @@ for e in ker[1:]:
         cur_e, last = e.time_range.end, e
 for g, a, b in sorted(edges, reverse=True)[:12]:
     print(f"   gap {g:7.1f} us  after {a}  before {b}")
+# per-launch durations of the tensor-core kernels of the LAST step, in launch order (diagnostic: which layers cost what in situ)
+if os.environ.get("TIMELINE_SEQ"):
+    per = len(ker) // K
+    last = ker[-per:]
+    for fam_name in ("conv_tc2_kernel", "wgrad_tc_kernel", "gn_bwd_kernel", "gn_fwd_kernel"):
+        seq = [round(e.time_range.end - e.time_range.start, 1) for e in last if fam_name in e.name]
+        print(fam_name, len(seq), seq)
