@@ -283,7 +283,11 @@ static int linear_small_launch(const ddpm_conv_args* a, cudaStream_t st) {
 // and the whole backward of one of them (dW, db and the accumulated d temb) in ONE launch instead of three.
 // 32x32 output tiles, inner tiles of 32, operands fetched through small functors so the same tile routine serves
 // row-major and transposed accesses.
-template <typename FA, typename FB>
+// KA / KB: the operand is contiguous along the INNER dimension in global memory -> consecutive threads fetch consecutive
+// inner indices (coalesced) and the 33-float row padding makes the transposing shared-memory write conflict-free; otherwise
+// consecutive threads fetch consecutive rows.  (Row-fastest fetches of a k-contiguous operand were 1024 strided 4-byte
+// loads per tile: the grouped time-proj forward took 80 us for 0.26 GFLOP.)
+template <bool KA, bool KB, typename FA, typename FB>
 __device__ __forceinline__ void tile_gemm32(FA fa, FB fb, int Kin, float acc[2][2], float (*As)[LBM + 1], float (*Bs)[LBN + 1]) {
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
     for (int k0 = 0; k0 < Kin; k0 += LBK) {
@@ -291,8 +295,10 @@ __device__ __forceinline__ void tile_gemm32(FA fa, FB fb, int Kin, float acc[2][
 #pragma unroll
         for (int j = 0; j < 4; ++j) {                       // 1024 elements per operand tile, 256 threads
             const int l = tid + j * 256;
-            As[l >> 5][l & 31] = fa(l & 31, k0 + (l >> 5));  // (row, k): consecutive threads -> consecutive rows
-            Bs[l >> 5][l & 31] = fb(l & 31, k0 + (l >> 5));
+            if (KA) As[l & 31][l >> 5] = fa(l >> 5, k0 + (l & 31));
+            else As[l >> 5][l & 31] = fa(l & 31, k0 + (l >> 5));
+            if (KB) Bs[l & 31][l >> 5] = fb(l >> 5, k0 + (l & 31));
+            else Bs[l >> 5][l & 31] = fb(l & 31, k0 + (l >> 5));
         }
         __syncthreads();
 #pragma unroll
@@ -315,9 +321,7 @@ __global__ void __launch_bounds__(256) linear_grouped_fwd_kernel(const float* __
     if (n0 >= e.N) return;
     const float* __restrict__ w = e.w;
     float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-    // x is read k-fastest per row in global memory; the tile loader walks rows fastest -> strided, but the whole
-    // operand (B x 512 fp32 = 256 KB) is L1/L2 resident and shared by every block
-    tile_gemm32([&](int r, int k) { const int m = m0 + r; float v = (m < M && k < K) ? x[(int64_t)m * xpitch + k] : 0.f; return a_silu ? silu_f(v) : v; },
+    tile_gemm32<true, true>([&](int r, int k) { const int m = m0 + r; float v = (m < M && k < K) ? x[(int64_t)m * xpitch + k] : 0.f; return a_silu ? silu_f(v) : v; },
                 [&](int r, int k) { const int n = n0 + r; return (n < e.N && k < K) ? __ldg(w + (int64_t)n * K + k) : 0.f; },
                 K, acc, As, Bs);
     const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
@@ -353,7 +357,7 @@ __global__ void __launch_bounds__(256) time_proj_bwd_kernel(const float* __restr
     float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
     if (r < tilesA_n) {                                      // ---- part A: weight (and bias) gradient, inner dim = batch
         const int n0 = r * LBM;
-        tile_gemm32([&](int rr, int b) { const int n = n0 + rr; return (n < N && b < B) ? dy[(int64_t)b * dpitch + n] : 0.f; },
+        tile_gemm32<false, false>([&](int rr, int b) { const int n = n0 + rr; return (n < N && b < B) ? dy[(int64_t)b * dpitch + n] : 0.f; },
                     [&](int rr, int b) { const int k = k0 + rr; return (k < K && b < B) ? silu_f(temb[(int64_t)b * K + k]) : 0.f; },
                     B, acc, As, Bs);
 #pragma unroll
@@ -369,7 +373,7 @@ __global__ void __launch_bounds__(256) time_proj_bwd_kernel(const float* __restr
         }
     } else {                                                 // ---- part B: d temb, inner dim = N
         const int b0 = (r - tilesA_n) * LBM;
-        tile_gemm32([&](int rr, int n) { const int b = b0 + rr; return (b < B && n < N) ? dy[(int64_t)b * dpitch + n] : 0.f; },
+        tile_gemm32<true, false>([&](int rr, int n) { const int b = b0 + rr; return (b < B && n < N) ? dy[(int64_t)b * dpitch + n] : 0.f; },
                     [&](int rr, int n) { const int k = k0 + rr; return (k < K && n < N) ? __ldg(w + (int64_t)n * K + k) : 0.f; },
                     N, acc, As, Bs);
 #pragma unroll
