@@ -708,3 +708,30 @@ def test_bf16_training_trajectory_tracks_the_fp32_oracle():
     assert num < 0.2 * den, (num, den)
     e_num = sum(float((s.float() - o_ema[k]).norm()) ** 2 for s, k in zip(ema.shadow, sd)) ** 0.5
     assert e_num < 0.2 * den, (e_num, den)
+
+
+def test_batched_weight_repack_matches_the_per_weight_kernel():
+    """WeightCache.repack_all (one tile-transposing launch for every packed copy, after the optimiser step) against
+    ddpm_pack_weights per weight: odd channel counts, channel padding, 3x3 / 1x1 / linear, fp32 and bf16 copies."""
+    from ddpm_diffusion_model_b200 import _lib, engine
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(5)
+    shapes = [((96, 3, 3, 3), 16, 0), ((192, 96, 3, 3), 0, 0), ((96, 288, 1, 1), 0, 0), ((100, 70, 3, 3), 80, 112),
+              ((384, 96), 0, 0), ((3, 96, 3, 3), 0, 16), ((33, 17, 1, 1), 32, 48)]
+    for dt in (_lib.BF16, _lib.F32):
+        cache = engine.WeightCache()
+        E = engine.Exec(dev, dt, True, True, wcache=cache)
+        ws = [torch.nn.Parameter(torch.randn(*s, device=dev)) for s, _, _ in shapes]
+        for w, (_, cip, cop) in zip(ws, shapes):
+            cache.get(E, w, dt, True, cip, cop)
+        with torch.no_grad():
+            for w in ws:
+                w.mul_(0.5).add_(0.25)                     # what an optimiser step does (same storage, new values)
+        assert cache.repack_all(E.stream)
+        got = [(cache.entries[(id(w), dt, cip, cop)][1].clone(), cache.entries[(id(w), dt, cip, cop)][2].clone())
+               for w, (_, cip, cop) in zip(ws, shapes)]
+        fresh = engine.WeightCache()
+        for w, (_, cip, cop), (gf, gd) in zip(ws, shapes, got):
+            rf, rd = fresh.get(E, w, dt, True, cip, cop)
+            torch.cuda.synchronize()
+            assert torch.equal(gf, rf) and torch.equal(gd, rd), (tuple(w.shape), cip, cop, dt)
