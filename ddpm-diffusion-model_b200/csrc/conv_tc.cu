@@ -552,7 +552,10 @@ struct Tc2Params {
                                   //    issue only the centre tap
 };
 
-template <int MT, int TAPS>
+// FUSED2: the 1x1 second operand (ddpm_conv_args.in2).  A template parameter, not a run-time branch: the extra stage kind
+// in the producer and MMA-issue loops cost 3-4 % on EVERY convolution when it was one (A/B of three builds on one box,
+// 96->96@64: 67.9 -> 70.0 us) -- the issue loop is that tight.
+template <int MT, int TAPS, bool FUSED2>
 __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                     const __grid_constant__ CUtensorMap tmB,
                                                                     const __grid_constant__ CUtensorMap tmA2,
@@ -561,7 +564,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_c
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* ring = smem;
     uint8_t* bres = ring + (size_t)p.S * p.stage_bytes;                                   // resident weights (b_res only)
-    uint64_t* bars = (uint64_t*)(bres + (p.b_res ? (size_t)(p.Cin / KC) * p.b_chunk_bytes + (size_t)p.KCH2 * p.b2_chunk_bytes : 0));
+    uint64_t* bars = (uint64_t*)(bres + (p.b_res ? (size_t)(p.Cin / KC) * p.b_chunk_bytes + (FUSED2 ? (size_t)p.KCH2 * p.b2_chunk_bytes : 0) : 0));
     uint64_t* full = bars;            uint64_t* empty = full + p.S;
     uint64_t* tfull = empty + p.S;    uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
@@ -572,7 +575,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_c
     const bool leader = rank == 0;
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
     const int KCH = p.Cin / KC;
-    const int NST = (KCH + p.KS - 1) / p.KS + p.KCH2;   // ring stages per item (KS = 1 whenever a second operand is fused)
+    const int KCH2 = FUSED2 ? p.KCH2 : 0;
+    const int NST = (KCH + p.KS - 1) / p.KS + KCH2;     // ring stages per item (KS = 1 whenever a second operand is fused)
     const int halo_rows = (p.taps == 9) ? p.Wp + 1 : 0;
     const int tile_rows = 128 * MT;
     const int cols_per_buf = MT * p.NT;
@@ -581,7 +585,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_c
         // descriptor fetch (128 B each from the parameter bank) overlaps barrier set-up / TMEM allocation / cluster sync
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-        if (p.KCH2) {
+        if (FUSED2) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA2) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB2) : "memory");
         }
@@ -614,8 +618,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_c
                 for (int st = 0; st < NST; ++st, ++g) {
                     const int s = g % p.S; const uint32_t ph = (g / p.S) & 1;
                     mbar_wait(&empty[s], ph ^ 1);
-                    const bool second = st >= NST - p.KCH2;                       // a chunk of the fused 1x1 operand
-                    const int kc0 = second ? st - (NST - p.KCH2) : st * p.KS, nk = second ? 1 : min(p.KS, KCH - kc0);
+                    const bool second = FUSED2 && st >= NST - KCH2;               // a chunk of the fused 1x1 operand
+                    const int kc0 = second ? st - (NST - KCH2) : st * p.KS, nk = second ? 1 : min(p.KS, KCH - kc0);
                     const uint32_t fbar = mapa_u32(smem_u32(&full[s]), 0);
                     const bool skipA = (p.exp & 1) && g >= (uint32_t)p.S, skipB = (p.exp & 2) && g >= (uint32_t)p.S;   // diagnostics
                     const bool loadB = !skipB && !(p.b_res && it != pair);       // resident weights arrive with the first item only
@@ -665,9 +669,9 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_c
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
                     uint32_t a_lo = ring_lo + s * stage16;
-                    if (st >= NST - p.KCH2) {
+                    if (FUSED2 && st >= NST - KCH2) {
                         // fused 1x1 operand: one MMA per M-tile, the patch's centre tap against the one-tap weight slab
-                        const uint32_t kc2 = (uint32_t)(st - (NST - p.KCH2));
+                        const uint32_t kc2 = (uint32_t)(st - (NST - KCH2));
                         const uint32_t b_lo = p.b_res ? bres_lo + (uint32_t)KCH * bchunk16 + kc2 * (uint32_t)(p.b2_chunk_bytes >> 4) : a_lo + a16;
                         const uint64_t bdesc = desc_pack(b_lo, hi);
 #pragma unroll
@@ -934,12 +938,13 @@ static int conv_tc2_launch(const ddpm_conv_args* a, cudaStream_t st) {
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     pdl_attr(at, &nat);
     cfg.attrs = at; cfg.numAttrs = nat;
-    static size_t configured[4] = {0, 0, 0, 0};
-#define TC2_GO(MTV, TAPSV, SLOT) { \
-        if (smem > configured[SLOT]) { CUDA_TRY(cudaFuncSetAttribute(conv_tc2_kernel<MTV, TAPSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured[SLOT] = smem; } \
-        CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<MTV, TAPSV>, tmA, tmB, p.KCH2 ? tmA2 : tmA, p.KCH2 ? tmB2 : tmB, p)); }
-    if (MT == 2) { if (p.taps == 9) TC2_GO(2, 9, 0) else TC2_GO(2, 1, 1) }
-    else { if (p.taps == 9) TC2_GO(1, 9, 2) else TC2_GO(1, 1, 3) }
+    static size_t configured[6] = {0, 0, 0, 0, 0, 0};
+#define TC2_GO(MTV, TAPSV, F2, SLOT) { \
+        if (smem > configured[SLOT]) { CUDA_TRY(cudaFuncSetAttribute(conv_tc2_kernel<MTV, TAPSV, F2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured[SLOT] = smem; } \
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<MTV, TAPSV, F2>, tmA, tmB, F2 ? tmA2 : tmA, F2 ? tmB2 : tmB, p)); }
+    if (p.KCH2) { if (MT == 2) TC2_GO(2, 9, true, 4) else TC2_GO(1, 9, true, 5) }
+    else if (MT == 2) { if (p.taps == 9) TC2_GO(2, 9, false, 0) else TC2_GO(2, 1, false, 1) }
+    else { if (p.taps == 9) TC2_GO(1, 9, false, 2) else TC2_GO(1, 1, false, 3) }
 #undef TC2_GO
     LAUNCH_OK();
     return 0;
