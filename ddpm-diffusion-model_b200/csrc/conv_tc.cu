@@ -683,9 +683,9 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_c
                         __syncwarp();
                         continue;
                     }
-                    const int nk = min(p.KS, KCH - st * p.KS);
+                    const int nk = TAPS == 9 ? 1 : min(p.KS, KCH - st * p.KS);      // 3x3: one K-chunk per stage, always
                     for (int k = 0; k < nk; ++k, a_lo += chunk16) {
-                        const uint32_t b_lo = p.b_res ? bres_lo + (uint32_t)(st * p.KS + k) * bchunk16 : a_lo + a16;
+                        const uint32_t b_lo = p.b_res ? bres_lo + (uint32_t)((TAPS == 9 ? st : st * p.KS) + k) * bchunk16 : a_lo + a16;
 #pragma unroll
                         for (int tap = 0; tap < TAPS; ++tap) {
                             const uint64_t bdesc = desc_pack(b_lo + (uint32_t)tap * b_tap, hi);
