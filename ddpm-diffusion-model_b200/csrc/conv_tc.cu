@@ -1078,8 +1078,8 @@ __global__ void __launch_bounds__(TC_THREADS) wgrad_tc_kernel(const __grid_const
             const uint64_t ones_desc = desc_pack(desc_lo(smem_u32(ones), 2048u), hi);
             const uint16_t relmask = (uint16_t)((1u << crank) | 1u);   // release the stage here and at the multicasting rank 0
             // two copies of the loop: a predicated-off bias MMA in the common loop cost 11 % (measured A/B)
-            auto run = [&](auto with_bias) {
-                constexpr bool BIAS = decltype(with_bias)::value;
+            auto run = [&](auto with_bias, auto with_three, auto with_cl3) {
+                constexpr bool BIAS = decltype(with_bias)::value, THREE = decltype(with_three)::value, CL3 = decltype(with_cl3)::value;
                 uint32_t acc = 0, accb = 0;
                 int kmod = ((s_beg * (WG_KQ / 16)) % ngrp);                 // (global K-step index) mod ngrp
                 for (int i = 0; i < nst; ++i) {
@@ -1091,7 +1091,7 @@ __global__ void __launch_bounds__(TC_THREADS) wgrad_tc_kernel(const __grid_const
                     for (int ks = 0; ks < WG_KQ / 16; ++ks) {
                         const uint64_t ydesc = desc_pack(y_lo + (uint32_t)(ks * 16 * 128 / 16), hi);
                         if (el) umma_bf16(tmem_base, ydesc, desc_pack(a_lo + (uint32_t)((ks * 16) * 8), hi), idesc, ks == 0 ? acc : 1u);
-                        if (three && el) {
+                        if (THREE && el) {
                             umma_bf16(tmem_base + (uint32_t)p.NT, ydesc, desc_pack(a_lo + (uint32_t)((ks * 16 + 1) * 8), hi), idesc, ks == 0 ? acc : 1u);
                             umma_bf16(tmem_base + (uint32_t)(2 * p.NT), ydesc, desc_pack(a_lo + (uint32_t)((ks * 16 + 2) * 8), hi), idesc, ks == 0 ? acc : 1u);
                         }
@@ -1101,11 +1101,17 @@ __global__ void __launch_bounds__(TC_THREADS) wgrad_tc_kernel(const __grid_const
                         }
                     }
                     acc = 1;
-                    if (el) { if (p.cl3) umma_commit_mc(&empty[s], relmask); else umma_commit(&empty[s]); }
+                    if (el) { if (CL3) umma_commit_mc(&empty[s], relmask); else umma_commit(&empty[s]); }
                     __syncwarp();
                 }
             };
-            if (do_bias) run(std::true_type{}); else run(std::false_type{});
+            // every run-time flag of the issue loop is a compile-time constant of its copy (the loop is that sensitive)
+            auto go = [&](auto b) {
+                if (!three) run(b, std::false_type{}, std::false_type{});
+                else if (p.cl3) run(b, std::true_type{}, std::true_type{});
+                else run(b, std::true_type{}, std::false_type{});
+            };
+            if (do_bias) go(std::true_type{}); else go(std::false_type{});
             if (el) umma_commit(acc_full);
             __syncwarp();
         }
