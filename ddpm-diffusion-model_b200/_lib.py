@@ -109,6 +109,7 @@ SIGNATURES = {
     "ddpm_set_tc_mode": [_i, _i],
     "ddpm_set_tc_v2": [_i],
     "ddpm_set_pdl": [_i],
+    "ddpm_abi_struct_sizes": [_vp, _i],
 }
 
 
@@ -123,6 +124,15 @@ def _load() -> C.CDLL:
         fn = getattr(lib, name)        # AttributeError if the ABI symbol is missing
         fn.argtypes = argtypes
         fn.restype = C.c_int64 if name in ("ddpm_launch_count", "ddpm_wgrad_workspace_bytes") else C.c_int
+    # the ctypes mirrors above must have exactly the layouts the library was compiled with (a silent mismatch would
+    # corrupt every launch): compare sizeof() struct by struct and refuse to load otherwise
+    mine = [("ddpm_tensor", Tensor), ("ddpm_conv_args", ConvArgs), ("ddpm_lin_entry", LinEntry), ("ddpm_wgrad_args", WgradArgs),
+            ("ddpm_pack_entry", PackEntry), ("ddpm_adam_hyper", AdamHyper)]
+    got = (C.c_int32 * len(mine))()
+    n = lib.ddpm_abi_struct_sizes(got, len(mine))
+    bad = [(nm, C.sizeof(t), int(got[i])) for i, (nm, t) in enumerate(mine) if i >= n or C.sizeof(t) != int(got[i])]
+    if bad:
+        raise ImportError(f"ddpm_b200: ABI struct layout mismatch between _lib.py and {path}: {bad} (rebuild: python __graft_entry__.py)")
     return lib
 
 

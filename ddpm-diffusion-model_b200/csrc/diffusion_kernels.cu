@@ -14,6 +14,13 @@ int64_t g_ddpm_launches = 0;
 static int pdl_default() { const char* e = getenv("DDPM_B200_PDL"); return !(e && e[0] == '0'); }
 int g_ddpm_pdl = pdl_default();
 extern "C" int ddpm_set_pdl(int on) { g_ddpm_pdl = on ? 1 : 0; return 0; }
+extern "C" int ddpm_abi_struct_sizes(int32_t* out, int n) {
+    const int32_t v[6] = {(int32_t)sizeof(ddpm_tensor), (int32_t)sizeof(ddpm_conv_args), (int32_t)sizeof(ddpm_lin_entry),
+                          (int32_t)sizeof(ddpm_wgrad_args), (int32_t)sizeof(ddpm_pack_entry), (int32_t)sizeof(ddpm_adam_hyper)};
+    int k = 0;
+    for (; out && k < n && k < 6; ++k) out[k] = v[k];
+    return k;
+}
 
 #define TMAX 1024
 #define NTAB 10

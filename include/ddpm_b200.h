@@ -42,6 +42,10 @@ int ddpm_abi_version(void);
 int ddpm_num_sms(int device, int* out);
 /* Returns and resets the count of kernels this library launched since the last call. */
 int64_t ddpm_launch_count(int reset);
+/* sizeof() of the six ABI structs in declaration order (ddpm_tensor, ddpm_conv_args, ddpm_lin_entry, ddpm_wgrad_args,
+ * ddpm_pack_entry, ddpm_adam_hyper) so that a binding can verify its own layouts when it loads the library (the Python
+ * mirror refuses to import on a mismatch).  Returns the number of entries written (<= n). */
+int ddpm_abi_struct_sizes(int32_t* out, int n);
 
 /* ---------------- schedule tables: difussion_class.py:46-68 (10 fp32 [T] buffers) ---------- */
 /* rows: 0 betas 1 alphas 2 alphas_cumprod 3 sqrt_ac 4 sqrt_1m_ac 5 ac_prev 6 post_var

@@ -312,3 +312,15 @@ def test_device_loader_epoch_order_matches_torch_dataloader():
     torch.manual_seed(9); a = DeviceLoader.epoch_order(n, True, None)
     torch.manual_seed(9); b = torch.cat([t[0] for t in DataLoader(TensorDataset(torch.arange(n)), batch_size=8, shuffle=True)])
     assert torch.equal(a, b)
+
+
+def test_abi_struct_layouts_match_the_library():
+    """The ctypes mirrors are checked against sizeof() inside the library at import; here field by field for the one
+    struct whose tail grew this round (ddpm_conv_args: in2 / w2 appended, nothing before them moved)."""
+    import ctypes as C
+    from ddpm_diffusion_model_b200 import _lib
+    got = (C.c_int32 * 6)()
+    assert _lib.lib.ddpm_abi_struct_sizes(got, 6) == 6
+    mine = [_lib.Tensor, _lib.ConvArgs, _lib.LinEntry, _lib.WgradArgs, _lib.PackEntry, _lib.AdamHyper]
+    assert [int(v) for v in got] == [C.sizeof(t) for t in mine]
+    assert _lib.ConvArgs.in2.offset + C.sizeof(_lib.Tensor) == _lib.ConvArgs.w2.offset and _lib.ConvArgs.bias_n.offset < _lib.ConvArgs.in2.offset
