@@ -964,7 +964,9 @@ static int conv_tc2_launch(const ddpm_conv_args* a, cudaStream_t st) {
 int wgrad_tc_supported(const ddpm_wgrad_args* a);
 #define WG_KQ 64          // pixels per pipeline stage (4 UMMA K-steps)
 #define WG_ROWS 72        // patch rows per stage (KQ + 2 shifts, rounded to 8)
+#ifndef WG_STAGES
 #define WG_STAGES 5
+#endif
 
 struct WgTcParams {
     float* ws;                  // [split][mtile][grp][128][3*NT]
