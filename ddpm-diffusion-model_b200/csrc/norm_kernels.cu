@@ -19,12 +19,6 @@ namespace cg = cooperative_groups;
 #ifndef GN_FWD_OCC
 #define GN_FWD_OCC 4              // 64 registers, no spills: 83 vs 91 us at 96@64 (B=128) against 3 CTAs/SM
 #endif
-#ifndef GN_FWD_U
-#define GN_FWD_U 4
-#endif
-#ifndef GN_BWD_U
-#define GN_BWD_U 1                // with GN_BWD_OCC 4: 64 registers; +4..11 % over U = 2 at 3 CTAs/SM (occupancy beats ILP here)
-#endif
 #ifndef GN_BWD_OCC
 #define GN_BWD_OCC 4
 #endif
@@ -171,8 +165,8 @@ __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.w
 //            ago and at most ~50 clusters are in flight -- and writes the result.
 // HBM traffic: forward 2 (read) + 2 (write) = 4 B/elem bf16, backward 4 + 2 = 6 B/elem (+2 when
 // accumulating into dx), instead of 6 and 10 for separate stats / apply launches.
-// Thread mapping: a thread owns one 16-byte channel vector position `cv` and walks pixels, U packets
-// in flight.  Halo pixels are never read or written.
+// Thread mapping: a thread owns one 16-byte channel vector position `cv` and walks pixels; its packets stream through a
+// private cp.async ring in shared memory (below).  Halo pixels are never read or written.
 // ================================================================================================
 struct GnP {
     TV x, dy, o;                 // forward: x -> o;  backward: x, dy -> o (= dx)
