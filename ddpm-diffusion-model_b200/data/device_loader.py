@@ -73,12 +73,17 @@ class DeviceLoader:
         torch.randperm(n, generator=g)
         return order
 
+    @staticmethod
+    def shard_order(order: torch.Tensor, rank: int, world: int) -> torch.Tensor:
+        """Rank `rank`'s share of one epoch: every world-th index of the common permutation (what DistributedSampler
+        does), equal counts on every rank (the tail that does not divide is dropped)."""
+        if world <= 1:
+            return order
+        per = order.numel() // world
+        return order[rank:per * world:world]
+
     def _order(self) -> torch.Tensor:
-        order = self.epoch_order(self.N, self.shuffle, self.generator)
-        if self.world > 1:
-            per = self.N // self.world                       # equal work per rank (the tail is dropped)
-            order = order[self.rank:per * self.world:self.world]
-        return order
+        return self.shard_order(self.epoch_order(self.N, self.shuffle, self.generator), self.rank, self.world)
 
     def __len__(self) -> int:
         n = self.N // self.world if self.world > 1 else self.N

@@ -324,3 +324,15 @@ def test_abi_struct_layouts_match_the_library():
     mine = [_lib.Tensor, _lib.ConvArgs, _lib.LinEntry, _lib.WgradArgs, _lib.PackEntry, _lib.AdamHyper]
     assert [int(v) for v in got] == [C.sizeof(t) for t in mine]
     assert _lib.ConvArgs.in2.offset + C.sizeof(_lib.Tensor) == _lib.ConvArgs.w2.offset and _lib.ConvArgs.bias_n.offset < _lib.ConvArgs.in2.offset
+
+
+def test_device_loader_shards_partition_the_epoch():
+    """Under data parallelism every rank walks a disjoint, equally sized share of the SAME permutation."""
+    from ddpm_diffusion_model_b200.data.device_loader import DeviceLoader
+    n, world = 103, 4
+    order = DeviceLoader.epoch_order(n, True, torch.Generator().manual_seed(3))
+    parts = [DeviceLoader.shard_order(order, r, world) for r in range(world)]
+    assert all(p.numel() == n // world for p in parts)
+    merged = torch.stack(parts, 1).reshape(-1)                    # interleave back
+    assert torch.equal(merged, order[:(n // world) * world])
+    assert torch.equal(DeviceLoader.shard_order(order, 0, 1), order)
