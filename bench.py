@@ -16,8 +16,15 @@ synthetic 64x64 images, data-parallel over N GPUs (weak scaling).  One "step" = 
              same with one call per step (host reads the loss after every step)
   roofline : the dominant kernel (implicit-GEMM convolution) timed alone with CUDA events on the
              launching stream, algorithmic FLOPs / time vs the measured bf16 peak
-  cpu_baseline / --impl reference : the oracle port of the reference (CPU, fp32, all host threads)
-             on a bounded sample (B=8, the reference's own CPU-runnable configs[0] shapes)
+  cpu_baseline / --impl reference : the UNMODIFIED reference (vendored byte-for-byte into git-ignored baseline/_ref by
+             tools/vendor_reference.py) on the host cores through its own API -- train_one_epoch(device="cpu") at the
+             arm's batch (B=128, bf16 CPU autocast = the function's default; fp32 beside it) and
+             ddim_infer_sample(steps=100, n=8); that process never imports the product package
+  gpu_eager_baseline : the same unmodified reference on the same B200 through PyTorch eager (cuDNN/cuBLAS/SDPA, bf16
+             autocast + GradScaler + channels_last + cudnn.benchmark) in a subprocess -- the kernel-for-kernel bar
+             (SURVEY.md section 2.2); `vs_gpu_eager` = ours / eager
+  configs  : the 256-px half of the metric (BASELINE configs[2..4]): CelebA256 UNet train (B=32/GPU), DDIM-100 and
+             DDPM-1000 sampling, batch-sharded over the ranks
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -85,49 +92,77 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# reference arm / CPU baseline: the oracle port on the host cores
+# reference arm / CPU baseline: the UNMODIFIED reference (baseline/_ref) on the host cores.  Nothing here imports the
+# product package or oracle/.
 # ------------------------------------------------------------------------------------------------
-def cpu_train_imgs_per_s(steps, warmup, batch=8):
-    """One optimiser step of the reference algorithm (oracle port, fp32, dropout off) at B=8, 64px."""
-    from oracle import ddpm_oracle as O
-    torch.manual_seed(0)
-    from ddpm_diffusion_model_b200.model.unet_backbone import build_unet_64x64   # parameter init only (CPU tensors)
-    sd = {k: v.detach().clone() for k, v in build_unet_64x64(**LOW_GPU).state_dict().items()}
-    spec = O.UNetSpec(in_channels=3, time_embed_dim=512, img_resolution=64, **dict(LOW_GPU, dropout=0.0))
-    tb = O.make_tables()
-    torch.manual_seed(7)
-    x0 = torch.empty(batch, 3, 64, 64).uniform_(-1, 1)
-    opt, ema = {}, {k: v.clone() for k, v in sd.items()}
-    times = []
-    for i in range(warmup + steps):
-        t = torch.randint(1, 1000, (batch,))
-        noise = torch.randn_like(x0)
-        t0 = time.perf_counter()
-        _, _, sd, opt, ema = O.train_step(sd, spec, tb, x0, t, noise, opt, ema, lr=2e-4, step=i + 1, grad_clip=1.0, ema_decay=0.9995)
-        if i >= warmup:
-            times.append(time.perf_counter() - t0)
-    dt = sum(times) / len(times)
-    return batch / dt, dt, torch.get_num_threads()
+def _ref_arm():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_ddpm_reference_arm", os.path.join(ROOT, "baseline", "reference_arm.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
+        return                                        # under torchrun only rank 0 times the host arm
+    RA = _ref_arm()
+    why = RA.available()
+    if why:
+        GUARD.emit(json.dumps({"impl": "reference", "unavailable": why}))
         return
-    steps = min(args.steps, 4)
-    warm = min(args.warmup, 1) if args.warmup else 0
-    ips, dt, cores = cpu_train_imgs_per_s(steps, max(1, warm))
+    cores = RA.set_host_threads()                     # explicit: torchrun exports OMP_NUM_THREADS=1
+    B = args.ref_batch
+    steps = max(1, min(args.steps, args.ref_max_steps))
+    warm = 1 if args.warmup else 0
+    ips, sec, loss = RA.cpu_train(B, steps, warm, use_autocast=True)
+    extra = {}
+    if not args.ref_quick:
+        ips32, sec32, _ = RA.cpu_train(min(B, 32), 1, 1, use_autocast=False)
+        extra["train_fp32"] = {"value": ips32, "unit": "img/s", "ms_per_step": sec32 * 1e3,
+                               "sample": f"1 optimiser step (after 1 warm-up) at B={min(B, 32)}, use_autocast=False"}
+        sps, dt, evals = RA.cpu_ddim(args.ref_ddim_n, 100)
+        extra["ddim100"] = {"value": sps, "unit": "samples/s", "steps": 100, "unet_evals": evals, "batch": args.ref_ddim_n, "img": 64,
+                            "dtype": "f32", "seconds": dt, "timed": "whole ddim_infer_sample(device='cpu') call incl. grid PNG"}
+    ddim_head = args.workload == "ddim" and "ddim100" in extra
+    sample = (f"{steps} optimiser steps (after {warm} warm-up) of train_one_epoch(device='cpu', use_autocast=True -> CPU bf16 "
+              f"autocast, the function's default) at B={B}, 64x64, dropout 0.1, AdamW+EMA+clip")
     line = {
-        "impl": "reference", "metric": "train_img_per_s", "value": ips, "unit": "img/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": max(1, warm), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "CelebA64 low-GPU UNet train step (AdamW+EMA+clip), oracle port of the reference on host CPU",
-                   "batch": 8, "img": 64},
-        "cpu_baseline": {"value": ips, "unit": "img/s", "cores": cores, "kind": "port",
-                         "sample": f"{steps} optimiser steps at B=8, 64x64, fp32, dropout off"},
-        "e2e": {"value": ips, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference",
+        "metric": "ddim100_samples_per_s" if ddim_head else "train_img_per_s",
+        "value": extra["ddim100"]["value"] if ddim_head else ips,
+        "unit": "samples/s" if ddim_head else "img/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": (extra["ddim100"]["seconds"] / 99 if ddim_head else sec) * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if ddim_head else "bf16 (CPU autocast)",
+        "data": "synthetic",
+        "config": {"workload": "CelebA64 low-GPU UNet (12.68M) " + ("DDIM-100 sampling" if ddim_head else
+                               "training step: bf16 autocast + AdamW + EMA + clip") + ", UNMODIFIED reference on host CPU",
+                   "batch_per_gpu": args.ref_ddim_n if ddim_head else B, "img": 64, "T": 1000,
+                   "reference_tree": RA.manifest_id(), "torch_threads": cores, "os_cpu_count": os.cpu_count()},
+        "cpu_baseline": {"value": extra["ddim100"]["value"] if ddim_head else ips, "unit": "samples/s" if ddim_head else "img/s",
+                         "cores": cores, "kind": "reference", "sample": "ddim_infer_sample(steps=100, n=%d)" % args.ref_ddim_n if ddim_head else sample},
+        "e2e": {"value": extra["ddim100"]["value"] if ddim_head else ips, "unit": "samples/s" if ddim_head else "img/s",
+                "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "loss": loss, **extra,
     }
     GUARD.emit(json.dumps(line))
+
+
+def _json_subprocess(cmd, timeout):
+    """Run a helper (reference arms) in its own process and parse the last JSON line of its stdout."""
+    try:
+        env = dict(os.environ)
+        for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "OMP_NUM_THREADS"):
+            env.pop(k, None)
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env, cwd=ROOT)
+        for ln in reversed(out.stdout.strip().splitlines()):
+            ln = ln.strip()
+            if ln.startswith("{"):
+                return json.loads(ln)
+        return {"unavailable": f"no JSON from {' '.join(cmd[-4:])} (rc {out.returncode}): {out.stderr[-200:]}"}
+    except Exception as ex:                           # noqa: BLE001
+        return {"unavailable": f"{type(ex).__name__}: {ex}"[:300]}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -170,14 +205,33 @@ def conv_roofline(device, batch, reps=5, shapes=None):
     return tot_f, tot_t, detail
 
 
-def run_ours(args):
-    import torch.distributed as dist
-    from ddpm_diffusion_model_b200 import _lib
+def _build_ours(config, dev):
     from ddpm_diffusion_model_b200.model.difussion_class import Diffusion
-    from ddpm_diffusion_model_b200.model.unet_backbone import build_unet_64x64
+    from ddpm_diffusion_model_b200.model.unet_backbone import UNetDenoiser, build_unet_64x64
     from ddpm_diffusion_model_b200.training_loops.ema import EMA
     from ddpm_diffusion_model_b200.training_loops.grad_scaler import make_grad_scaler
-    from ddpm_diffusion_model_b200.training_loops.train_one_epoch import train_one_epoch
+    torch.manual_seed(0)
+    if config == "celeba256":
+        # BASELINE.json configs[2]: CelebA256 attention UNet (63.1 M params), bf16, batch 32 per GPU
+        model = UNetDenoiser(3, 128, (1, 1, 2, 2, 4), 2, {16}, 512, 0.1, 4, 64, 256).to(dev)
+        opt = torch.optim.AdamW(model.parameters(), lr=2e-4, betas=(0.9, 0.999), weight_decay=0.005)
+        ema_decay, gf_train, img = 0.9997, 1257.3, 256
+    else:
+        model = build_unet_64x64(**LOW_GPU).to(dev)
+        opt = torch.optim.AdamW(model.parameters(), lr=2e-4, betas=(0.9, 0.999), weight_decay=0.0)
+        ema_decay, gf_train, img = 0.9995, TRAIN_GF_PER_IMG, 64
+    diff = Diffusion(T=1000, schedule="linear", beta_min=1e-4, beta_max=2e-2, img_size=img).to(dev)
+    return model, diff, opt, EMA(model, decay=ema_decay), make_grad_scaler("cuda", True), gf_train, img
+
+
+def run_ours(args):
+    import contextlib
+    import io
+    import tempfile
+    import torch.distributed as dist
+    from ddpm_diffusion_model_b200 import _lib
+    from ddpm_diffusion_model_b200 import engine as _engine
+    from ddpm_diffusion_model_b200.training_loops.train_one_epoch import last_step_losses, train_one_epoch
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -186,54 +240,48 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    B = args.batch
     if args.tc_exp:
         _lib.lib.ddpm_set_tc_mode(1 | (args.tc_exp << 4), 0)
-    torch.manual_seed(0)
     c256 = args.config == "celeba256"
-    IMG = 256 if c256 else 64
+    B = 32 if (c256 and args.batch == 128) else args.batch
+    model, diff, opt, ema, scaler, gf_train, IMG = _build_ours(args.config, dev)
     if c256:
-        # BASELINE.json configs[2]: CelebA256 attention UNet (63.1 M params), bf16, batch 32 per GPU
-        from ddpm_diffusion_model_b200.model.unet_backbone import UNetDenoiser
-        if args.batch == 128:
-            B = 32
-        model = UNetDenoiser(3, 128, (1, 1, 2, 2, 4), 2, {16}, 512, 0.1, 4, 64, 256).to(dev)
-        opt = torch.optim.AdamW(model.parameters(), lr=2e-4, betas=(0.9, 0.999), weight_decay=0.005)
-        ema_decay, gf_train = 0.9997, 1257.3
         args.no_ddim = True
-    else:
-        model = build_unet_64x64(**LOW_GPU).to(dev)
-        opt = torch.optim.AdamW(model.parameters(), lr=2e-4, betas=(0.9, 0.999), weight_decay=0.0)
-        ema_decay, gf_train = 0.9995, TRAIN_GF_PER_IMG
-    diff = Diffusion(T=1000, schedule="linear", beta_min=1e-4, beta_max=2e-2, img_size=IMG).to(dev)
-    ema = EMA(model, decay=ema_decay)
-    scaler = make_grad_scaler("cuda", True)
     torch.manual_seed(7 + rank)
     x_host = torch.empty(B, 3, IMG, IMG).uniform_(-1, 1).pin_memory()
     y_host = torch.zeros(B)
     x_dev = x_host.to(dev)
+    kw = dict(scaler=scaler, ema=ema, device=f"cuda:{local}", grad_clip=1.0)
 
     # One `train_one_epoch` call over a K-batch loader is the reference API's unit of work (train_one_epoch.py:11);
     # inside it nothing synchronises with the host until the epoch's mean loss is read, so the enqueue of step i+1
-    # overlaps the GPU work of step i.  (One call PER step drains the GPU at every call boundary: +2.5 ms/step of
-    # idle GPU, measured with tools/step_timeline.py; reported below as `sync_every_step`.)
+    # overlaps the GPU work of step i.  (One call PER step drains the GPU at every call boundary; reported below as
+    # `sync_every_step`.)
     def step_resident(K=1):
-        return train_one_epoch(model, diff, [(x_dev, y_host)] * K, opt, scaler=scaler, ema=ema, device=f"cuda:{local}", grad_clip=1.0)
+        return train_one_epoch(model, diff, [(x_dev, y_host)] * K, opt, **kw)
 
     # e2e: every step copies its batch from pinned host memory (x.to(device, non_blocking=True) inside the loop,
     # train_one_epoch.py:62) and DMAs its 4-byte loss back into a pinned trace (`last_step_losses()`).
     def step_e2e(K=1):
-        return train_one_epoch(model, diff, [(x_host, y_host)] * K, opt, scaler=scaler, ema=ema, device=f"cuda:{local}", grad_clip=1.0)
+        return train_one_epoch(model, diff, [(x_host, y_host)] * K, opt, **kw)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def max_over_ranks(v):
+        if world > 1:
+            tt = torch.tensor([v], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt)
+        return v
+
     def timed(fn, K, per_call=False):
         barrier()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         _lib.launch_count(reset=True)
+        t0 = time.perf_counter()
         s.record()
         last = None
         if per_call:
@@ -242,14 +290,11 @@ def run_ours(args):
         else:
             last = fn(K)
         e.record()
+        host_s = time.perf_counter() - t0              # host time to ENQUEUE the K steps (+ the final loss read)
         barrier()
         ms = s.elapsed_time(e)
         n_launch = _lib.launch_count(reset=True)
-        if world > 1:
-            tt = torch.tensor([ms], device=dev)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            ms = float(tt)
-        return ms / 1e3, n_launch, last
+        return max_over_ranks(ms) / 1e3, n_launch, last, host_s
 
     if args.profile:                                  # short run for `ncu` launch lists
         for _ in range(2):
@@ -261,17 +306,15 @@ def run_ours(args):
         torch.cuda.nvtx.range_pop()
         return
     step_resident(max(3, args.warmup))
-    from ddpm_diffusion_model_b200 import engine as _engine
     miss0 = _engine.POOL.misses
     with ClockSampler(local) as clk:
-        sec, launches, last = timed(step_resident, args.steps)
+        sec, launches, last, host_s = timed(step_resident, args.steps)
     pool_misses = _engine.POOL.misses - miss0
     step_e2e(2)
-    sec_e2e, _, last_e2e = timed(step_e2e, args.steps)
-    from ddpm_diffusion_model_b200.training_loops.train_one_epoch import last_step_losses
+    sec_e2e, _, last_e2e, _ = timed(step_e2e, args.steps)
     trace = last_step_losses()
     assert trace.numel() == args.steps and bool(torch.isfinite(trace).all()), "per-step loss trace incomplete"
-    sec_sync, _, _ = timed(step_e2e, min(args.steps, 20), per_call=True)
+    sec_sync, _, _, _ = timed(step_e2e, min(args.steps, 20), per_call=True)
     sec_sync /= min(args.steps, 20)
     value = world * B * args.steps / sec
     e2e = world * B * args.steps / sec_e2e
@@ -280,42 +323,43 @@ def run_ours(args):
     from ddpm_diffusion_model_b200.data import DeviceLoader
     u8 = torch.randint(0, 256, (B * args.steps, IMG, IMG, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(3 + rank))
     feeder = DeviceLoader(u8, B, shuffle=True, drop_last=True, device=dev, generator=torch.Generator().manual_seed(5), shard=False)
-    sec_feed, _, _ = timed(lambda K: train_one_epoch(model, diff, feeder, opt, scaler=scaler, ema=ema, device=f"cuda:{local}",
-                                                     grad_clip=1.0), args.steps)
+    sec_feed, _, _, _ = timed(lambda K: train_one_epoch(model, diff, feeder, opt, **kw), args.steps)
     del feeder, u8
 
-    # ---- second half of the metric: DDIM-100 samples/s through the public sampler (bf16 autocast, eta = 0,
-    # batch-sharded over ranks with no communication; includes the grid PNG write of the reference API)
-    ddim = None
-    if not args.no_ddim:
-        import tempfile
+    def sampler_leg(mdl, dff, kind, nb, img, steps):
+        """Whole public sampler call (bf16 autocast, eta = 0, batch-sharded over ranks with no communication; includes
+        the grid PNG write of the reference API).  Wall clock, barrier + synchronize on both sides, max over ranks."""
         from ddpm_diffusion_model_b200.testing.ddpim_inference import ddim_infer_sample
-        nb = args.ddim_batch
-        outp = os.path.join(tempfile.gettempdir(), f"ddim_bench_{rank}.png")
+        from ddpm_diffusion_model_b200.testing.ddpm_inference import ddpm_infer_sample
+        outp = os.path.join(tempfile.gettempdir(), f"{kind}_bench_{rank}.png")
 
-        def ddim_call():
+        def call(n_steps):
             with torch.autocast("cuda", dtype=torch.bfloat16):
-                ddim_infer_sample(model, diff, n=nb * world, img_size=64, device=f"cuda:{local}", ema=None, out_path=outp,
-                                  seed=1234, steps=100, eta=0.0, shard=world > 1)
-        import contextlib, io
+                if kind == "ddim":
+                    ddim_infer_sample(mdl, dff, n=nb * world, img_size=img, device=f"cuda:{local}", ema=None, out_path=outp,
+                                      seed=1234, steps=n_steps, eta=0.0, shard=world > 1)
+                else:
+                    ddpm_infer_sample(mdl, dff, n=nb * world, img_size=img, device=f"cuda:{local}", ema=None, out_path=outp,
+                                      seed=1234, shard=world > 1)
         with contextlib.redirect_stdout(io.StringIO()):
-            ddim_call()                                   # warm-up (captures nothing persistent; pools / packs warm)
+            if kind == "ddim":
+                call(min(steps, 12))                              # warm-up: pools / packed weights / schedule handle
             barrier()
             t0 = time.perf_counter()
-            ddim_call()
+            call(steps)
             barrier()
-            dt_ddim = time.perf_counter() - t0
-        if world > 1:
-            tt = torch.tensor([dt_ddim], device=dev)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dt_ddim = float(tt)
-        ddim = {"value": nb * world / dt_ddim, "unit": "samples/s", "steps": 100, "unet_evals": 99, "batch_per_gpu": nb,
-                "img": 64, "dtype": "bf16 autocast", "ms_per_eval": dt_ddim / 99 * 1e3,
+            dt = max_over_ranks(time.perf_counter() - t0)
+        evals = steps - 1 if kind == "ddim" else dff.T
+        mdl.train()
+        return {"value": nb * world / dt, "unit": "samples/s", "steps": steps if kind == "ddim" else dff.T, "unet_evals": evals,
+                "batch_per_gpu": nb, "img": img, "dtype": "bf16 autocast", "ms_per_eval": dt / evals * 1e3, "seconds": dt,
                 "cuda_graph": os.environ.get("DDPM_B200_GRAPHS", "0") == "1",
-                "timed": "whole ddim_infer_sample call (wall clock, barrier + synchronize both sides), incl. grid PNG"}
-        model.train()
+                "timed": "whole %s_infer_sample call (wall clock, barrier + synchronize both sides), incl. grid PNG" % kind}
 
-    roof = cpu = None
+    # ---- second half of the metric: DDIM-100 samples/s through the public sampler
+    ddim = None if args.no_ddim else sampler_leg(model, diff, "ddim", args.ddim_batch, IMG, 100)
+
+    roof = cpu = eager = None
     if rank == 0:
         pk = peaks()
         fl, tt, detail = conv_roofline(dev, B, shapes=C256_SHAPES if c256 else None)
@@ -329,11 +373,71 @@ def run_ours(args):
                 "kernel": "conv_tc2_kernel (tcgen05 cta_group::2 implicit GEMM; 3x3 s1 layers of the %s UNet, count-weighted, B=%d)" % ("CelebA256" if c256 else "low-GPU", B),
                 "peak_source": pk["src"] + " bf16 burst (kernel timed alone)", "per_shape": detail,
                 "step_tensor_frac": (gf_train * 1e9 * world * B * args.steps / sec) / (world * pk["tf_sus"] * 1e12)}
-        if world == 1 and not args.no_cpu:
-            ips, dt, cores = cpu_train_imgs_per_s(2, 1)
-            cpu = {"value": ips, "unit": "img/s", "cores": cores, "kind": "port",
-                   "sample": "2 optimiser steps (after 1 warm-up) of the oracle port at B=8, 64x64, fp32"}
+
+    # ---- the 256-px half of the metric (BASELINE configs[2..4]); the 64-px model and its buffers are released first
+    configs = None
+    if not c256 and not args.no_c256:
+        del model, diff, opt, ema, scaler, kw
+        _engine.POOL.clear()
+        torch.cuda.empty_cache()
+        m2, d2, o2, e2, s2, gf2, _ = _build_ours("celeba256", dev)
+        B2 = args.c256_batch
+        torch.manual_seed(11 + rank)
+        x2 = torch.empty(B2, 3, 256, 256).uniform_(-1, 1).pin_memory()
+        y2 = torch.zeros(B2)
+        kw2 = dict(scaler=s2, ema=e2, device=f"cuda:{local}", grad_clip=1.0)
+        K2 = max(3, min(args.steps, args.c256_steps))
+        train_one_epoch(m2, d2, [(x2, y2)] * 3, o2, **kw2)
+        sec2, launches2, last2, _ = timed(lambda K: train_one_epoch(m2, d2, [(x2, y2)] * K, o2, **kw2), K2)
+        configs = {"celeba256_train": {
+            "metric": "train_img_per_s", "value": world * B2 * K2 / sec2, "unit": "img/s", "ms_per_step": sec2 / K2 * 1e3, "steps": K2,
+            "batch_per_gpu": B2, "img": 256, "params": 63100675, "dtype": "bf16", "gpu_launches": launches2, "loss": last2[0],
+            "train_tflops_per_gpu": gf2 * 1e9 * B2 * K2 / sec2 / 1e12,
+            "step_tensor_frac": (gf2 * 1e9 * B2 * K2 / sec2) / (peaks()["tf_sus"] * 1e12),
+            "timed": "one train_one_epoch call over K pinned HOST batches (H2D of the batch + D2H of the loss every step), CUDA events, max over ranks"}}
+        del o2, e2, s2, kw2, x2
+        m2.zero_grad(set_to_none=True)
+        _engine.POOL.clear()
+        torch.cuda.empty_cache()
+        configs["celeba256_ddim100"] = sampler_leg(m2, d2, "ddim", args.c256_ddim_batch, 256, 100)
+        if not args.no_ddpm:
+            _engine.POOL.clear()
+            torch.cuda.empty_cache()
+            configs["celeba256_ddpm1000"] = sampler_leg(m2, d2, "ddpm", args.c256_ddpm_batch, 256, 1000)
+        del m2, d2
+        _engine.POOL.clear()
+        torch.cuda.empty_cache()
+
+    if rank == 0 and world == 1:
+        py = sys.executable
+        if not args.no_cpu:
+            # bounded sample of the UNMODIFIED reference on this box's host cores (own process: no product code mapped)
+            r = _json_subprocess([py, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                                  "--ref-quick", "--ref-batch", "32"], 600)
+            cpu = r.get("cpu_baseline") if "cpu_baseline" in r else {"value": None, "unit": "img/s", "cores": None, "kind": "reference",
+                                                                       "sample": r.get("unavailable", "failed")}
+        if not args.no_eager:
+            # the same unmodified reference on THIS B200 through PyTorch eager -- the kernel-for-kernel bar
+            eager = {"low64": _json_subprocess([py, os.path.join(ROOT, "baseline", "reference_arm.py"), "gpu", "low64", str(B),
+                                                 str(min(args.steps, 10)), str(0 if args.no_ddim else args.ddim_batch), "100"], 900)}
+            if configs is not None:
+                eager["celeba256"] = _json_subprocess([py, os.path.join(ROOT, "baseline", "reference_arm.py"), "gpu", "celeba256",
+                                                       str(args.c256_batch), "5", str(args.c256_ddim_batch), "100"], 900)
     if rank == 0:
+        vs_eager = None
+        if eager:
+            vs_eager = {}
+            lo = eager.get("low64", {})
+            if "train" in lo:
+                vs_eager["train_e2e"] = e2e / lo["train"]["value"]
+                vs_eager["train_device"] = value / lo["train"]["value"]
+            if ddim and "ddim" in lo:
+                vs_eager["ddim100"] = ddim["value"] / lo["ddim"]["value"]
+            hi = eager.get("celeba256", {})
+            if configs and "train" in hi:
+                vs_eager["celeba256_train"] = configs["celeba256_train"]["value"] / hi["train"]["value"]
+            if configs and "ddim" in hi:
+                vs_eager["celeba256_ddim100"] = configs["celeba256_ddim100"]["value"] / hi["ddim"]["value"]
         line = {
             "metric": "train_img_per_s", "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True,
@@ -352,9 +456,11 @@ def run_ours(args):
                                                "gather+ToTensor+Normalize kernel per step)"},
                     "sync_every_step": {"value": world * B / sec_sync, "ms_per_step": sec_sync * 1e3,
                                         "timed": "one train_one_epoch call PER step (host reads the loss after every step)"}},
-            "gpu_launches": launches, "clocks": clk.summary(), "roofline": roof, "cpu_baseline": cpu,
+            "gpu_launches": launches, "host_enqueue_ms_per_step": host_s / args.steps * 1e3,
+            "clocks": clk.summary(), "roofline": roof, "cpu_baseline": cpu,
             "loss": last[0] if last else None, "pool_misses_in_timed_region": pool_misses, "ddim100": ddim,
             "train_tflops_per_gpu": gf_train * 1e9 * B * args.steps / sec / 1e12,
+            "configs": configs, "gpu_eager_baseline": eager, "vs_gpu_eager": vs_eager,
         }
         GUARD.emit(json.dumps(line))
     if world > 1:
@@ -386,6 +492,19 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="train", choices=["train", "ddim"],
+                    help="--impl reference: which half of the metric is the line's headline value (the other is a field)")
+    ap.add_argument("--ref-batch", type=int, default=128, help="--impl reference: batch of the host train step (the arm's B)")
+    ap.add_argument("--ref-max-steps", type=int, default=3, help="--impl reference: cap on timed host steps (bounded sample)")
+    ap.add_argument("--ref-ddim-n", type=int, default=8, help="--impl reference: images of the host DDIM-100 leg")
+    ap.add_argument("--ref-quick", action="store_true", help="--impl reference: bf16 train leg only (cpu_baseline of our line)")
+    ap.add_argument("--no-eager", action="store_true", help="skip the gpu_eager_baseline legs (reference on this B200, PyTorch eager)")
+    ap.add_argument("--no-c256", action="store_true", help="skip the 256-px block (CelebA256 train / DDIM-100 / DDPM-1000)")
+    ap.add_argument("--no-ddpm", action="store_true", help="skip DDPM-1000 @256 (the longest leg, ~45 s)")
+    ap.add_argument("--c256-batch", type=int, default=32)
+    ap.add_argument("--c256-steps", type=int, default=8)
+    ap.add_argument("--c256-ddim-batch", type=int, default=16)
+    ap.add_argument("--c256-ddpm-batch", type=int, default=64)
     ap.add_argument("--batch", type=int, default=128)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--config", default="low64", choices=["low64", "celeba256"],

@@ -155,5 +155,18 @@ def call(name: str, *args) -> None:
     check(getattr(lib, name)(*args), name)
 
 
+def stream_for(device) -> int:
+    """Current CUDA stream handle of `device` for a C-ABI call.  The entry points launch on the process's CURRENT
+    device (kernels, the constant-bank uploads of the schedule tables, memsets), so tensors on another GPU would be
+    processed by the wrong device's kernels -- torch ops guard against that, a plain C ABI cannot.  Refuse loudly."""
+    import torch
+    idx = device.index if getattr(device, "index", None) is not None else torch.cuda.current_device()
+    cur = torch.cuda.current_device()
+    if idx != cur:
+        raise RuntimeError(f"ddpm_b200: tensors live on cuda:{idx} but the current device is cuda:{cur}; call "
+                           f"torch.cuda.set_device({idx}) (or use `with torch.cuda.device({idx}):`) before using the model")
+    return torch.cuda.current_stream(device).cuda_stream
+
+
 def launch_count(reset: bool = False) -> int:
     return int(lib.ddpm_launch_count(1 if reset else 0))

@@ -132,7 +132,9 @@ extern "C" int ddpm_param_update(float* p, const float* g, float* m, float* v, f
 }
 
 // torch.amp.GradScaler.update (_amp_update_scale_) on the scaler's own _scale / _growth_tracker tensors
-__global__ void scaler_update_kernel(float* scale, int* tracker, const float* stats, float growth, float backoff, int interval) {
+// stats[2] <- the scale this step's gradients carried (read by the host-side grad-norm diagnostic AFTER the update)
+__global__ void scaler_update_kernel(float* scale, int* tracker, float* stats, float growth, float backoff, int interval) {
+    stats[2] = scale[0];
     if (stats[1] != 0.0f) { scale[0] *= backoff; tracker[0] = 0; }
     else {
         int t = tracker[0] + 1;
@@ -140,7 +142,7 @@ __global__ void scaler_update_kernel(float* scale, int* tracker, const float* st
         tracker[0] = t;
     }
 }
-extern "C" int ddpm_scaler_update(float* scale, int32_t* tracker, const float* stats, float growth, float backoff,
+extern "C" int ddpm_scaler_update(float* scale, int32_t* tracker, float* stats, float growth, float backoff,
                                   int interval, void* stream) {
     if (!scale || !tracker || !stats || interval <= 0) return DDPM_E_ARG;
     scaler_update_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(scale, tracker, stats, growth, backoff, interval);

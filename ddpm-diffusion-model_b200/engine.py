@@ -212,7 +212,7 @@ class Exec:
         self.rng = rng
         self.prefer_tc = 1 if prefer_tc else 0
         self.use_tc = bool(prefer_tc) and dt == _lib.BF16     # tcgen05 kernels (channel padding to 16)
-        self.stream = torch.cuda.current_stream(device).cuda_stream
+        self.stream = _lib.stream_for(device)
 
     # ---- allocation helpers
     def act(self, N, H, W, C, halo=1) -> Act:

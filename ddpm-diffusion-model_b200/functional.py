@@ -53,9 +53,15 @@ def compute_dtype(x: torch.Tensor) -> tuple:
 
 def make_exec(x: torch.Tensor, module: torch.nn.Module, need_grad: bool) -> engine.Exec:
     dt, _ = compute_dtype(x)
-    E = engine.Exec(x.device, dt, module.training, need_grad, rng=rng_state(x.device))
+    shared = rng_state(x.device)
+    E = engine.Exec(x.device, dt, module.training, need_grad, rng=shared)
     if module.training:
-        _lib.call("ddpm_rng_advance", E.rng.data_ptr(), E.stream)
+        _lib.call("ddpm_rng_advance", shared.data_ptr(), E.stream)
+        # The dropout masks of THIS call are a function of {seed, step} as they are now.  Backward rebuilds the masks from
+        # E.rng, so it must see this call's step, not whatever the shared counter has advanced to by then (a second
+        # training-mode forward before backward: chained stand-alone ResBlocks, two model(x) calls summed, a no_grad
+        # forward in between).  A 16-byte device-side snapshot per call, stream-ordered after the advance.
+        E.rng = shared.clone()
     return E
 
 

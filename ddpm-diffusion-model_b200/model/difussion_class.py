@@ -37,7 +37,7 @@ def _cuda_only(x: torch.Tensor, what: str):
 
 
 def _stream(x: torch.Tensor) -> int:
-    return torch.cuda.current_stream(x.device).cuda_stream
+    return _lib.stream_for(x.device)
 
 
 class _MSE(torch.autograd.Function):

@@ -85,6 +85,6 @@ def render_denoise_strip_ddim(model, diffusion, *, img_size: int = 64, device: s
             x = diffusion.p_sample_step_ddim(model, x_t=x, t=t, t_prev=tp, eta=eta, clip_x0=True, noise=None)
             if cur in wanted:
                 frames.append(to_image01(x)[0])
-        grid = save_grid(torch.stack(frames, 0).cpu(), len(frames), out_path, pad)
+        grid = save_grid(torch.stack(frames, 0), len(frames), out_path, pad)     # frames stay on the GPU; one D2H inside
         print(f"[DENOISE-DDIM] strip 1×{len(frames)} guardado → {out_path} (steps={len(sched)}, eta={eta})")
     return grid

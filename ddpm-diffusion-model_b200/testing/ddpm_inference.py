@@ -51,7 +51,6 @@ def render_denoise_strip(model, diffusion, *, img_size: int = 64, device: str = 
             x = diffusion.p_sample_step(model, x, t)
             if i in wanted:
                 frames.append(to_image01(x)[0])           # stays on the GPU; one D2H at the end
-        strip = torch.stack(frames, 0).cpu()
-        grid = save_grid(strip, len(frames), out_path, pad)
+        grid = save_grid(torch.stack(frames, 0), len(frames), out_path, pad)
         print(f"[DENOISE] strip 1×{len(frames)} guardado → {out_path}")
     return grid

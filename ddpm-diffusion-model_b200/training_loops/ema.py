@@ -8,7 +8,7 @@ from ..arena import ensure_arena
 
 
 def _stream(dev) -> int:
-    return torch.cuda.current_stream(dev).cuda_stream
+    return _lib.stream_for(dev)
 
 
 class EMA:
@@ -69,14 +69,17 @@ class EMA:
 
     @torch.no_grad()
     def copy_to(self, model):
+        from ..engine import GLOBAL_WCACHE
         if self._flat_ok(model):
             self._arena.flat.copy_(self._flat)
-            from ..engine import GLOBAL_WCACHE
             GLOBAL_WCACHE.bump()
             return
         for i, p in enumerate(model.parameters()):
             if p.requires_grad:
                 p.data.copy_(self.shadow[i].data)
+        # `.data.copy_` does not bump Tensor._version: without this the packed bf16/fp32 weight copies of the
+        # convolution kernels would stay at the pre-swap weights (the flat branch above does the same)
+        GLOBAL_WCACHE.bump()
 
     @torch.no_grad()
     def state_dict(self):

@@ -21,7 +21,7 @@ from .training_utils import compute_grad_norm, gpu_mem_mb
 
 
 def _stream(dev) -> int:
-    return torch.cuda.current_stream(dev).cuda_stream
+    return _lib.stream_for(dev)
 
 
 class _LossTrace:
@@ -129,6 +129,7 @@ class FusedStep:
             if ema is not None:
                 ema.update(self.model)
         if use_scaler:
+            # (the kernel also records stats[2] = the scale THIS step's gradients carried, for grad_norm())
             _lib.call("ddpm_scaler_update", scaler._scale.data_ptr(), scaler._growth_tracker.data_ptr(),
                       self.stats.data_ptr(), float(scaler.get_growth_factor()), float(scaler.get_backoff_factor()),
                       int(scaler.get_growth_interval()), st)
@@ -137,8 +138,9 @@ class FusedStep:
 
     def grad_norm(self, scaler, use_scaler: bool) -> float:
         """||g||_2 of the unscaled gradients from the last reduction (diagnostic; one host sync)."""
-        s = float(scaler._scale.item()) if use_scaler else 1.0
-        return float(self.stats[0].item()) ** 0.5 / s
+        st = self.stats.tolist()                       # [sum g^2, found_inf, scale used by this step, -]
+        s = st[2] if (use_scaler and st[2] > 0.0) else 1.0
+        return st[0] ** 0.5 / s
 
 
 def _get_fused(model, optimizer, arena) -> FusedStep:

@@ -267,8 +267,9 @@ int ddpm_param_update(float* p, const float* g, float* m, float* v, float* ema, 
                       const float* stats, float* step, const float* scale, const ddpm_adam_hyper* h,
                       void* stream);
 /* GradScaler.update() on its own tensors: scale *= backoff on inf, *= growth after `interval`
- * clean steps (tracker: int32 [1]). */
-int ddpm_scaler_update(float* scale, int32_t* tracker, const float* stats, float growth, float backoff,
+ * clean steps (tracker: int32 [1]).  Also records stats[2] = the scale before the update (the one this
+ * step's gradients carried), so a later grad-norm read-back divides by the right factor. */
+int ddpm_scaler_update(float* scale, int32_t* tracker, float* stats, float growth, float backoff,
                        int interval, void* stream);
 /* For optimisers other than Adam(W): g *= clip/scale in place (g = 0 when inf was found). */
 int ddpm_grad_unscale_clip(float* g, int64_t n, const float* stats, const float* scale, float max_norm,

@@ -57,6 +57,13 @@ def test_conv_tc_matches_simt(mods, case):
         assert relerr(y_tc.buf.t, y_ref.buf.t) < 1e-2
         full = y_tc.buf.t.float()
         assert float(full[:, 0].abs().max() + full[:, -1].abs().max() + full[:, :, 0].abs().max() + full[:, :, -1].abs().max()) == 0
+        if not accum:
+            # independent leg: ATen fp32 on the same bf16-rounded operands (the tcgen05 path must not only agree with the
+            # repo's own CUDA-core kernel)
+            ref = torch.nn.functional.conv2d(x.interior().float().permute(0, 3, 1, 2), w.detach().bfloat16().float(), b,
+                                             stride=s, padding=k // 2)
+            ref = ref + tb[:, :, None, None] + r.interior().float().permute(0, 3, 1, 2)
+            assert relerr(y_tc.interior().float().permute(0, 3, 1, 2), ref) < 1e-2
 
 
 FUSED = [  # N, Cmain, Cin2, Cout, H  -- out = conv3x3(a; w) + conv1x1(x2; w2) + bias, the ResBlock's conv2 + skip
@@ -130,6 +137,10 @@ def test_wgrad_tc_matches_simt(mods, case):
     ref_b = dy.interior().float().sum((0, 1, 2))[:co_v]
     assert relerr(b1.grad, ref_b) < 1e-3
     assert relerr(b2.grad / 2, ref_b) < 1e-3
+    # independent leg: ATen's fp32 weight gradient of the same bf16-rounded operands
+    ref_w = torch.nn.grad.conv2d_weight(x.interior().float().permute(0, 3, 1, 2).contiguous(), (Co, Ci, k, k),
+                                        dy.interior().float().permute(0, 3, 1, 2).contiguous(), padding=k // 2)
+    assert relerr(w2.grad / 2, ref_w[:co_v, :ci_v]) < 1e-2
 
 
 def test_downsample_grads_via_zero_upsample(mods):

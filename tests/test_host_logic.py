@@ -336,3 +336,52 @@ def test_device_loader_shards_partition_the_epoch():
     merged = torch.stack(parts, 1).reshape(-1)                    # interleave back
     assert torch.equal(merged, order[:(n // world) * world])
     assert torch.equal(DeviceLoader.shard_order(order, 0, 1), order)
+
+
+# ------------------------------------------------------------------------------------------------
+# baseline arms: the unmodified reference, vendored; the reference process maps no product code
+# ------------------------------------------------------------------------------------------------
+def test_vendored_reference_is_byte_identical_and_untracked():
+    import hashlib
+    import json
+    import subprocess
+    ref = "/root/reference/src"
+    man = os.path.join(ROOT, "baseline", "_ref", "MANIFEST.json")
+    if not os.path.isdir(ref):
+        if not os.path.exists(man):
+            pytest.skip("no /root/reference and no vendored copy")
+    else:
+        subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "vendor_reference.py")])
+    files = json.load(open(man))["files"]
+    assert len(files) >= 16 and "src/training_loops/train_one_epoch.py" in files
+    for rel_path, sha in files.items():
+        got = hashlib.sha256(open(os.path.join(ROOT, "baseline", "_ref", rel_path), "rb").read()).hexdigest()
+        assert got == sha, rel_path
+        if os.path.isdir(ref):
+            assert hashlib.sha256(open(os.path.join("/root/reference", rel_path), "rb").read()).hexdigest() == sha
+    tracked = subprocess.run(["git", "-C", ROOT, "ls-files", "baseline/_ref"], capture_output=True, text=True).stdout.strip()
+    assert tracked == "", "baseline/_ref must stay out of the history"
+
+
+def test_reference_arm_runs_the_reference_and_never_imports_the_product():
+    """`bench.py --impl reference` (tiny bounded sample): the line says kind=reference, and the process that produced it
+    has neither the product package nor the oracle nor libddpm_b200.so mapped."""
+    import json
+    import subprocess
+    if not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "src")):
+        pytest.skip("reference not vendored")
+    code = (
+        "import sys, json, runpy, os\n"
+        f"sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '0', '--ref-quick', '--ref-batch', '2']\n"
+        f"runpy.run_path({os.path.join(ROOT, 'bench.py')!r}, run_name='__main__')\n"
+        "bad = [m for m in sys.modules if m.startswith('ddpm_diffusion_model_b200') or m.startswith('oracle')]\n"
+        "maps = open('/proc/self/maps').read()\n"
+        "sys.stderr.write('CHECK ' + json.dumps({'bad': bad, 'so': 'libddpm_b200' in maps}) + '\\n')\n"
+    )
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "reference" and line["value"] > 0
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["config"]["reference_tree"] != "unknown"
+    chk = json.loads([ln for ln in out.stderr.splitlines() if ln.startswith("CHECK ")][-1][6:])
+    assert chk == {"bad": [], "so": False}, chk
