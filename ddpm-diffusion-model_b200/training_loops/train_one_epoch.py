@@ -52,6 +52,15 @@ class _LossTrace:
 _TRACE = _LossTrace()
 
 
+_ENQUEUE = {"seconds": 0.0, "batches": 0}
+
+
+def last_enqueue_ms_per_step() -> float:
+    """Host time the most recent `train_one_epoch` call spent ENQUEUING one micro-batch (loop body only, before the one
+    synchronising read of the loss sum at the end): the number that must stay below the GPU time of a step."""
+    return 1e3 * _ENQUEUE["seconds"] / max(1, _ENQUEUE["batches"])
+
+
 def last_step_losses() -> torch.Tensor:
     """Losses of every micro-batch of the most recent `train_one_epoch` call (fp32, CPU)."""
     return _TRACE.values()
@@ -197,6 +206,7 @@ def train_one_epoch(model, diffusion, dataloader, optimizer, *, scaler=None, ema
             _header(probe_timesteps)
         did_header = True
 
+    t_loop = time.perf_counter()
     for i, (x, _) in enumerate(dataloader):
         if (max_batches is not None) and (i >= max_batches):
             break
@@ -281,5 +291,6 @@ def train_one_epoch(model, diffusion, dataloader, optimizer, *, scaler=None, ema
                 continue
             raise
 
+    _ENQUEUE["seconds"], _ENQUEUE["batches"] = time.perf_counter() - t_loop, n_seen_batches
     avg_loss = float(loss_sum.item()) / max(1, n_seen_batches)
     return avg_loss, n_seen_batches, n_seen_images, global_step
