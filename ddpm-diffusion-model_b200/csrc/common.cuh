@@ -121,6 +121,13 @@ __device__ __forceinline__ float dsilu_half(float h) {
     return fmaf(s, h * (1.0f - t), s);
 }
 
+// same with the 1/(1-p) of a following dropout folded into the constants: hs = 0.5 / (1 - p)
+__device__ __forceinline__ float dsilu_half_scaled(float h, float hs) {
+    const float t = tanh_approx(h);
+    const float s = fmaf(hs, t, hs);
+    return fmaf(s, h * (1.0f - t), s);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

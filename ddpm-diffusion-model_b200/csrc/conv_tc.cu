@@ -351,6 +351,15 @@ static int encode(CUtensorMap* m, void* base, int rank, const uint64_t* dims, co
     return r == CUDA_SUCCESS ? 0 : 1;   // cudaErrorInvalidValue
 }
 
+// shared with norm_kernels.cu (slab GroupNorm): bf16 tiled tensor map, swizzle_bytes in {0, 32, 64, 128}
+int ddpm_encode_tiled_bf16(CUtensorMap* m, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                           const uint32_t* box, int swizzle_bytes) {
+    int rc = get_encode(); if (rc) return rc;
+    const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+    return encode(m, base, rank, dims, strides_bytes, box, sw);
+}
+
 static int pick_nt(int Cout) {
     if (Cout <= 256) return Cout;
     for (int nt = 256; nt >= 64; nt -= 16) if (Cout % nt == 0) return nt;

@@ -32,11 +32,23 @@ def shard_range(n: int, rank: Optional[int] = None, world_size: Optional[int] = 
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def make_buckets(numel: int, bucket_elems: int) -> List[Tuple[int, int]]:
-    """[start, end) element ranges covering the arena from its END to its START (backward order)."""
+def make_buckets(numel: int, bucket_elems: int, tail_elems: int = 0, tail_bucket_elems: int = 0) -> List[Tuple[int, int]]:
+    """[start, end) element ranges covering the arena from its END to its START (backward order).
+
+    The gradients at the START of the arena (in_conv, time_mlp, the first encoder level) become final last, so whatever
+    bucket holds them cannot be hidden behind backward: its all-reduce is the exposed tail in front of the optimiser
+    pass.  With `tail_elems` > 0 the first `tail_elems` elements are therefore cut into small buckets of
+    `tail_bucket_elems` -- the reduction of all but the last small piece still overlaps the end of backward, and the
+    exposed piece is a few hundred KB instead of a full bucket."""
     out, end = [], numel
+    tail_elems = min(max(0, tail_elems), numel)
+    while end > tail_elems:
+        start = max(tail_elems, end - bucket_elems)
+        out.append((start, end))
+        end = start
+    step = max(1, tail_bucket_elems or bucket_elems)
     while end > 0:
-        start = max(0, end - bucket_elems)
+        start = max(0, end - step)
         out.append((start, end))
         end = start
     return out
@@ -49,11 +61,17 @@ class GradSync:
     report completion through `progress(module)` (engine.unet_backward) and a bucket is reduced as
     soon as every span that intersects it is final.  `progress(None)` / `finish()` flush the rest."""
 
-    def __init__(self, flat_grad: torch.Tensor, module_spans: dict, bucket_bytes: int = 16 << 20, group=None):
+    def __init__(self, flat_grad: torch.Tensor, module_spans: dict, bucket_bytes: int = 16 << 20, group=None,
+                 tail_bytes: Optional[int] = None, tail_bucket_bytes: Optional[int] = None):
+        import os
         self.g = flat_grad
         self.group = group
         self.spans = module_spans
-        self.buckets = make_buckets(flat_grad.numel(), max(1, bucket_bytes // 4))
+        if tail_bytes is None:
+            tail_bytes = int(os.environ.get("DDPM_B200_DP_TAIL_MB", "12")) << 20
+        if tail_bucket_bytes is None:
+            tail_bucket_bytes = int(os.environ.get("DDPM_B200_DP_TAIL_BUCKET_KB", "2048")) << 10
+        self.buckets = make_buckets(flat_grad.numel(), max(1, bucket_bytes // 4), tail_bytes // 4, max(1, tail_bucket_bytes // 4))
         self.cuda = flat_grad.is_cuda
         self.comm = torch.cuda.Stream(flat_grad.device) if self.cuda else None
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1

@@ -138,6 +138,12 @@ int ddpm_gn_bwd_colsum(const ddpm_tensor* x, int dtype, int groups, const double
                        const float* beta, float eps, int act, float p_drop, const uint64_t* rng,
                        uint32_t layer_id, const ddpm_tensor* dy, const ddpm_tensor* dx, int accumulate,
                        float* dgamma, float* dbeta, float* colsum_nc, float* colsum_c, int dy_scratch, void* stream);
+/* Kernel selection for the bf16 GroupNorm forward (fused) / backward: 0 (default) = the streaming kernels; 1 = the CTA's
+ * rows of an image arrive by bulk tensor copy, stay in shared memory between the statistics and the apply phase and
+ * leave by bulk tensor store / reduce-add where they fit ("slab" kernels: every tensor crosses HBM once); 2 = slab
+ * kernels without 16-CTA clusters.  The slab kernels measured slower on B200 and are kept for
+ * A/B measurements; results are the same up to fp32 summation order (and one extra bf16 rounding when dx accumulates). */
+int ddpm_set_gn_slab(int mode);
 
 /* nearest x2 (unet_backbone.py:63) and its adjoint (2x2 sum) */
 int ddpm_upsample2x(const ddpm_tensor* x, const ddpm_tensor* out, int dtype, void* stream);

@@ -170,6 +170,11 @@ def test_shard_range_partitions():
             assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
     b = make_buckets(1000, 300)
     assert b == [(700, 1000), (400, 700), (100, 400), (0, 100)]
+    # graded buckets: the start of the arena (the gradients that become final LAST) is cut into small pieces so that
+    # only a small all-reduce is exposed in front of the optimiser pass
+    b = make_buckets(1000, 300, tail_elems=250, tail_bucket_elems=100)
+    assert b == [(700, 1000), (400, 700), (250, 400), (150, 250), (50, 150), (0, 50)]
+    assert make_buckets(100, 300, tail_elems=5000, tail_bucket_elems=40) == [(60, 100), (20, 60), (0, 20)]
 
 
 def _free_port():
@@ -191,7 +196,8 @@ def _dp_worker(rank, world, port, q):
             pass
         mods = [M() for _ in range(5)]
         spans = {id(m): (100 + 180 * i, 100 + 180 * (i + 1)) for i, m in enumerate(mods)}
-        gs = GradSync(g, spans, bucket_bytes=4 * 256)
+        gs = GradSync(g, spans, bucket_bytes=4 * 256, tail_bytes=4 * 300, tail_bucket_bytes=4 * 64)
+        assert len(gs.buckets) == 3 + 5 and gs.buckets[-1] == (0, 44)
         gs.begin()
         launched = []
         for m in reversed(mods):                         # backward order: highest offsets first
@@ -203,7 +209,7 @@ def _dp_worker(rank, world, port, q):
         ok = torch.allclose(g, full.mean(0), atol=1e-6)
         # a micro-batch that does not step must not communicate
         g2 = full[rank].clone()
-        gs2 = GradSync(g2, spans, bucket_bytes=4 * 256)
+        gs2 = GradSync(g2, spans, bucket_bytes=4 * 256, tail_bytes=0)
         gs2.reset()
         for m in reversed(mods):
             gs2.progress(m)

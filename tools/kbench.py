@@ -22,6 +22,7 @@ ap.add_argument("--epi", action="store_true", help="conv: also time with bias + 
 ap.add_argument("--v1", action="store_true", help="conv: also time the first-generation kernel")
 ap.add_argument("--gnshape", default=None, help="restrict gn to one 'C,H'")
 ap.add_argument("--tcexp", type=int, default=0, help="experiment flags for the whole run (ddpm_set_tc_mode(1 | flags << 4)), e.g. 512 = wgrad with (1,3,1) clusters + dY multicast")
+ap.add_argument("--gnslab", default="1", help="gn: comma list of ddpm_set_gn_slab modes to time (0 streaming, 1 slab, 2 slab without 16-CTA clusters)")
 ap.add_argument("--shape", default=None, help="restrict conv/wgrad to one 'Cin,Cout,H' (for ncu)")
 args = ap.parse_args()
 only = set(args.only.split(","))
@@ -125,21 +126,26 @@ if "wgrad" in only:
         del x, dy
 
 if "gn" in only:
+  for slab_mode in [int(v) for v in args.gnslab.split(",")]:
+    _lib.lib.ddpm_set_gn_slab(slab_mode)
+    print(f"--- gn, ddpm_set_gn_slab({slab_mode})", flush=True)
     for c, hw, cnt in GN:
-        gn = torch.nn.GroupNorm(32, c, eps=1e-6).to(dev)
-        x = E.act(B, hw, hw, c); x.interior().normal_()
-        o = E.act(B, hw, hw, c)
-        dy = E.act(B, hw, hw, c); dy.interior().normal_()
-        dx = E.act(B, hw, hw, c)
-        n = B * hw * hw * c
-        fl = n * 2 > (100 << 20)            # flush L2 between reps only when the tensor would not fit anyway
-        st = engine.gn_stats(E, x, 32)
-        report("gn", f"stats {c}@{hw}", timeit(lambda: engine.gn_stats(E, x, 32), flush=fl), nbytes=2 * n, cnt=cnt)
-        report("gn", f"apply+silu {c}@{hw}", timeit(lambda: engine.gn_apply(E, x, st, gn, 1, 0.0, 0, out=o), flush=fl), nbytes=4 * n, cnt=cnt)
-        report("gn", f"FUSED fwd silu+drop {c}@{hw}", timeit(lambda: engine.gn_fwd(E, x, gn, 1, 0.1, 3, out=o), flush=fl), nbytes=4 * n, cnt=cnt)
-        report("gn", f"apply+silu+drop {c}@{hw}", timeit(lambda: engine.gn_apply(E, x, st, gn, 1, 0.1, 3, out=o), flush=fl), nbytes=4 * n, cnt=cnt)
-        report("gn", f"bwd(silu+drop) {c}@{hw}", timeit(lambda: engine.gn_bwd(E, x, st, gn, 1, 0.1, 3, dy, dx, False, dy_scratch=True), flush=fl), nbytes=6 * n, cnt=cnt)
-        del x, o, dy, dx
+          gn = torch.nn.GroupNorm(32, c, eps=1e-6).to(dev)
+          x = E.act(B, hw, hw, c); x.interior().normal_()
+          o = E.act(B, hw, hw, c)
+          dy = E.act(B, hw, hw, c); dy.interior().normal_()
+          dx = E.act(B, hw, hw, c)
+          n = B * hw * hw * c
+          fl = n * 2 > (100 << 20)            # flush L2 between reps only when the tensor would not fit anyway
+          st = engine.gn_stats(E, x, 32)
+          report("gn", f"stats {c}@{hw}", timeit(lambda: engine.gn_stats(E, x, 32), flush=fl), nbytes=2 * n, cnt=cnt)
+          report("gn", f"apply+silu {c}@{hw}", timeit(lambda: engine.gn_apply(E, x, st, gn, 1, 0.0, 0, out=o), flush=fl), nbytes=4 * n, cnt=cnt)
+          report("gn", f"FUSED fwd silu+drop {c}@{hw}", timeit(lambda: engine.gn_fwd(E, x, gn, 1, 0.1, 3, out=o), flush=fl), nbytes=4 * n, cnt=cnt)
+          report("gn", f"apply+silu+drop {c}@{hw}", timeit(lambda: engine.gn_apply(E, x, st, gn, 1, 0.1, 3, out=o), flush=fl), nbytes=4 * n, cnt=cnt)
+          report("gn", f"bwd(silu+drop) {c}@{hw}", timeit(lambda: engine.gn_bwd(E, x, st, gn, 1, 0.1, 3, dy, dx, False, dy_scratch=True), flush=fl), nbytes=6 * n, cnt=cnt)
+          report("gn", f"skip bwd accumulate {c}@{hw}", timeit(lambda: engine.gn_bwd(E, x, st, gn, 1, 0.0, 0, dy, dx, True, dy_scratch=True), flush=fl), nbytes=8 * n, cnt=cnt)
+          report("gn", f"skip FUSED fwd silu (eval) {c}@{hw}", timeit(lambda: engine.gn_fwd(E, x, gn, 1, 0.0, 0, out=o), flush=fl), nbytes=4 * n, cnt=cnt)
+          del x, o, dy, dx
 
 if "colsum" in only:
     for c, hw, cnt in [(96, 64, 12), (192, 32, 12), (192, 16, 12), (192, 8, 20)]:
