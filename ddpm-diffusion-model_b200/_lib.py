@@ -12,7 +12,7 @@ from . import build as _build
 
 F32, BF16 = 0, 1
 CLAMP_X0, DYN_THRESH = 1, 2
-CONV_NORMAL, CONV_TRANSPOSED = 0, 1
+CONV_NORMAL, CONV_TRANSPOSED, CONV_UP2X_PHASE = 0, 1, 2
 EPI_ACCUM, EPI_DSILU = 1, 2
 
 
@@ -28,7 +28,8 @@ class ConvArgs(C.Structure):
                 ("tbias", C.c_void_p), ("tbias_pitch", C.c_int32), ("res", Tensor), ("z", Tensor),
                 ("KH", C.c_int32), ("KW", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32),
                 ("mode", C.c_int32), ("a_silu", C.c_int32), ("epi", C.c_int32), ("dtype", C.c_int32),
-                ("prefer_tc", C.c_int32), ("bias_n", C.c_int32), ("in2", Tensor), ("w2", C.c_void_p)]
+                ("prefer_tc", C.c_int32), ("bias_n", C.c_int32), ("in2", Tensor), ("w2", C.c_void_p),
+                ("up_phase", C.c_int32)]
 
 
 class WgradArgs(C.Structure):
@@ -95,6 +96,7 @@ SIGNATURES = {
     "ddpm_wgrad_workspace_bytes": [C.POINTER(WgradArgs)],
     "ddpm_pack_weights": [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp],
     "ddpm_pack_weights_batched": [_vp, _i, _vp],
+    "ddpm_pack_weights_up2x": [_vp, _i, _i, _vp, _i, _vp],
     "ddpm_linear_grouped_fwd": [_vp, _i, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp],
     "ddpm_time_proj_bwd": [_vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _vp],
     "ddpm_attn_fwd": [_TP, _TP, _i, _i, _vp, _i, _vp],

@@ -23,6 +23,12 @@ extern "C" int ddpm_conv(const ddpm_conv_args* a, void* stream) {
     } else if (a->mode == DDPM_CONV_TRANSPOSED) {
         // out is the (larger) input-gradient; in is dY.  in.H must be the fwd conv's output size.
         if (a->in.H != (a->out.H + 2 * (a->KH - 1 - a->pad) - a->KH) / a->stride + 1) return DDPM_E_ARG;
+    } else if (a->mode == DDPM_CONV_UP2X_PHASE) {
+        // folded nearest-x2 + conv3x3: `in` is the low-resolution tensor, `out` the full-resolution view; tensor cores only
+        if (a->out.H != 2 * a->in.H || a->out.W != 2 * a->in.W || a->KH != 2 || a->KW != 2 || a->stride != 1) return DDPM_E_ARG;
+        if (a->up_phase < 0 || a->up_phase > 3 || a->res.ptr || a->z.ptr || a->in2.ptr || a->a_silu) return DDPM_E_ARG;
+        if (!a->prefer_tc || g_force_simt || !conv_tc_supported(a)) return DDPM_E_ARG;
+        return conv_tc_launch(a, (cudaStream_t)stream);
     } else return DDPM_E_ARG;
     if (a->res.ptr && (!tensor_ok(&a->res) || a->res.C != a->out.C || a->res.H != a->out.H || a->res.W != a->out.W)) return DDPM_E_ARG;
     if (a->z.ptr && (!tensor_ok(&a->z) || a->z.C != a->out.C || a->z.H != a->out.H || a->z.W != a->out.W)) return DDPM_E_ARG;

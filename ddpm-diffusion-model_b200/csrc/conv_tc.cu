@@ -368,11 +368,14 @@ static int pick_nt(int Cout) {
 
 int g_tc_v2_flag();
 int conv_tc_supported(const ddpm_conv_args* a) {
-    if (a->dtype != DDPM_BF16 || a->mode != DDPM_CONV_NORMAL || a->a_silu || a->z.ptr) return 0;
-    if (!((a->KH == 3 && a->KW == 3 && a->pad == 1) || (a->KH == 1 && a->KW == 1 && a->pad == 0))) return 0;
+    const bool up = a->mode == DDPM_CONV_UP2X_PHASE;
+    if (a->dtype != DDPM_BF16 || (a->mode != DDPM_CONV_NORMAL && !up) || a->a_silu || a->z.ptr) return 0;
+    if (up) { if (a->KH != 2 || a->KW != 2 || a->stride != 1 || !g_tc_v2_flag() || g_tc_mode != 1 || a->res.ptr || a->in2.ptr || (a->epi & DDPM_EPI_ACCUM)) return 0; }
+    else if (!((a->KH == 3 && a->KW == 3 && a->pad == 1) || (a->KH == 1 && a->KW == 1 && a->pad == 0))) return 0;
     const ddpm_tensor &in = a->in, &out = a->out;
     if (in.halo != 1 || out.halo != 1 || in.N != out.N) return 0;
-    if (a->stride == 1) { if (in.H != out.H || in.W != out.W) return 0; }
+    if (up) { if (out.H != 2 * in.H || out.W != 2 * in.W) return 0; }
+    else if (a->stride == 1) { if (in.H != out.H || in.W != out.W) return 0; }
     else if (a->stride == 2) { if (a->KH != 3 || (in.H & 1) || (in.W & 1) || out.H * 2 != in.H || out.W * 2 != in.W) return 0; }
     else return 0;
     if (in.C % 16 || out.C % 16 || in.pitch % 8 || out.pitch % 8) return 0;
@@ -556,6 +559,8 @@ struct Tc2Params {
     int v256;                     // out (and res) rows are 32-byte aligned -> 256-bit loads / stores
     int b_res;                    // 1: this CTA's half of the weight tile (all K-chunks, all taps) stays resident in shared
                                   //    memory -- loaded once, with the first item's stages -- and only A patches stream
+    int up, py, px;               // DDPM_CONV_UP2X_PHASE: 2x2 taps at rows y+ty+py-1 / columns x+tx+px-1 of the low-resolution input,
+                                  //    results stored at (2y+py, 2x+px) of the full-resolution output
     int KCH2;                     // K-chunks of the fused 1x1 second operand (0: none): they follow the 3x3 chunks of every
     int b2_chunk_bytes;           //    item, load their patch through tmA2 / their one-tap weight slab through tmB2 and
                                   //    issue only the centre tap
@@ -586,7 +591,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_c
     const int KCH = p.Cin / KC;
     const int KCH2 = FUSED2 ? p.KCH2 : 0;
     const int NST = (KCH + p.KS - 1) / p.KS + KCH2;     // ring stages per item (KS = 1 whenever a second operand is fused)
-    const int halo_rows = (p.taps == 9) ? p.Wp + 1 : 0;
+    const int halo_rows = (p.taps > 1) ? p.Wp + 1 : 0;
     const int tile_rows = 128 * MT;
     const int cols_per_buf = MT * p.NT;
 
@@ -661,7 +666,9 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_c
             const uint32_t hi = desc_hi(256u, 6u);                       // SBO 256 B, SWIZZLE_32B
             uint32_t tapoff[TAPS];                                       // A row shift of each tap, in 16-byte units
 #pragma unroll
-            for (int tap = 0; tap < TAPS; ++tap) tapoff[tap] = TAPS == 9 ? (uint32_t)(((tap / 3) * p.Wp + (tap % 3)) * 2) : 0u;
+            for (int tap = 0; tap < TAPS; ++tap)
+                tapoff[tap] = TAPS == 9 ? (uint32_t)(((tap / 3) * p.Wp + (tap % 3)) * 2)
+                            : TAPS == 4 ? (uint32_t)((((tap >> 1) + p.py) * p.Wp + ((tap & 1) + p.px)) * 2) : 0u;
             const uint32_t b_tap = (uint32_t)p.NT;                       // (NT/2 rows * 32 B) >> 4
             const uint32_t chunk16 = (uint32_t)((p.a_chunk_bytes + (p.b_res ? 0 : p.b_chunk_bytes)) >> 4), a16 = (uint32_t)(p.a_chunk_bytes >> 4);
             const uint32_t ring_lo = desc_lo(smem_u32(ring), 16u), stage16 = (uint32_t)(p.stage_bytes >> 4);
@@ -692,9 +699,9 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_c
                         __syncwarp();
                         continue;
                     }
-                    const int nk = TAPS == 9 ? 1 : min(p.KS, KCH - st * p.KS);      // 3x3: one K-chunk per stage, always
+                    const int nk = TAPS > 1 ? 1 : min(p.KS, KCH - st * p.KS);       // 3x3 / 2x2: one K-chunk per stage, always
                     for (int k = 0; k < nk; ++k, a_lo += chunk16) {
-                        const uint32_t b_lo = p.b_res ? bres_lo + (uint32_t)((TAPS == 9 ? st : st * p.KS) + k) * bchunk16 : a_lo + a16;
+                        const uint32_t b_lo = p.b_res ? bres_lo + (uint32_t)((TAPS > 1 ? st : st * p.KS) + k) * bchunk16 : a_lo + a16;
 #pragma unroll
                         for (int tap = 0; tap < TAPS; ++tap) {
                             const uint64_t bdesc = desc_pack(b_lo + (uint32_t)tap * b_tap, hi);
@@ -742,6 +749,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_c
                     y = yp - 1; x = xp - 1;
                     valid = y >= 0 && y < p.H && x >= 0 && x < p.W;
                     if (p.sub) { valid = valid && ((y | x) & 1) == 0; y >>= 1; x >>= 1; }
+                    if (p.up) { y = 2 * y + p.py; x = 2 * x + p.px; }
                 }
                 orow_a[mt] = valid ? p.out.at<bf16>(n, y, x, n0) : nullptr;
                 rrow_a[mt] = (valid && p.has_res && !(p.exp & 16)) ? p.res.at<bf16>(n, y, x, n0) : nullptr;   // exp bit 4: timing-only
@@ -872,6 +880,7 @@ static int conv_tc2_launch(const ddpm_conv_args* a, cudaStream_t st) {
     if (!(g_tc_exp & 32) && p.NT % 32 == 0 && p.NT > 128) p.NT /= 2;
     p.n_tiles = p.Cout / p.NT;
     p.taps = a->KH * a->KW;
+    p.up = a->mode == DDPM_CONV_UP2X_PHASE ? 1 : 0; p.py = p.up ? (a->up_phase >> 1) : 0; p.px = p.up ? (a->up_phase & 1) : 0;
     p.Hp = a->in.H + 2; p.Wp = a->in.W + 2; p.H = a->in.H; p.W = a->in.W;
     p.Qtot = a->in.N * p.Hp * p.Wp;
     p.accum = (a->epi & DDPM_EPI_ACCUM) ? 1 : 0;
@@ -883,7 +892,7 @@ static int conv_tc2_launch(const ddpm_conv_args* a, cudaStream_t st) {
     int MT = 256 / p.NT; if (MT > 2) MT = 2; if (MT < 1) MT = 1;
     // small problems: prefer more, smaller items so that every SM pair gets one
     if (MT == 2 && (int64_t)ceil_div(p.Qtot, 512) * p.n_tiles < sm_count() / 2) MT = 1;
-    const int halo_rows = p.taps == 9 ? p.Wp + 1 : 0;
+    const int halo_rows = p.taps > 1 ? p.Wp + 1 : 0;
     {
         int need = 128 * MT + 2 * halo_rows;
         int nseg = (need + 255) / 256;
@@ -893,7 +902,7 @@ static int conv_tc2_launch(const ddpm_conv_args* a, cudaStream_t st) {
     p.a_chunk_bytes = (p.P * 32 + 255) & ~255;
     p.b_chunk_bytes = p.taps * (p.NT / 2) * 32;             // multiple of 256: NT/2 is a multiple of 8
     const int KCH = p.Cin / KC;
-    p.KS = p.taps == 9 ? 1 : (KCH < 4 ? KCH : 4);
+    p.KS = p.taps > 1 ? 1 : (KCH < 4 ? KCH : 4);
     p.KCH2 = a->in2.ptr ? a->in2.C / KC : 0;                // fused 1x1 second operand (3x3 main conv only: KS == 1)
     p.b2_chunk_bytes = (p.NT / 2) * 32;
     const int budget = 212 * 1024;
@@ -903,7 +912,7 @@ static int conv_tc2_launch(const ddpm_conv_args* a, cudaStream_t st) {
     // Weights resident in shared memory when this CTA's half tile (all K-chunks, all taps) leaves room for a >= 3-deep
     // A ring and every CTA pair sees several items: then only activations stream (14.8 instead of 30.8 B/clk/SM at NT=96).
     p.b_res = 0;
-    if (p.taps == 9 && !(g_tc_exp & 64)) {
+    if (p.taps > 1 && !(g_tc_exp & 64)) {
         const int bres_bytes = KCH * p.b_chunk_bytes + p.KCH2 * p.b2_chunk_bytes;
         const int pr = pairs - pairs % p.n_tiles;             // a pair keeps ONE channel tile: pairs must be a multiple of n_tiles
         if (bres_bytes + 3 * p.a_chunk_bytes <= budget && pr >= p.n_tiles && p.items >= 3 * pr) { p.b_res = 1; pairs = pr; }
@@ -947,11 +956,12 @@ static int conv_tc2_launch(const ddpm_conv_args* a, cudaStream_t st) {
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     pdl_attr(at, &nat);
     cfg.attrs = at; cfg.numAttrs = nat;
-    static size_t configured[6] = {0, 0, 0, 0, 0, 0};
+    static size_t configured[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #define TC2_GO(MTV, TAPSV, F2, SLOT) { \
         if (smem > configured[SLOT]) { CUDA_TRY(cudaFuncSetAttribute(conv_tc2_kernel<MTV, TAPSV, F2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured[SLOT] = smem; } \
         CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<MTV, TAPSV, F2>, tmA, tmB, F2 ? tmA2 : tmA, F2 ? tmB2 : tmB, p)); }
     if (p.KCH2) { if (MT == 2) TC2_GO(2, 9, true, 4) else TC2_GO(1, 9, true, 5) }
+    else if (p.taps == 4) { if (MT == 2) TC2_GO(2, 4, false, 6) else TC2_GO(1, 4, false, 7) }
     else if (MT == 2) { if (p.taps == 9) TC2_GO(2, 9, false, 0) else TC2_GO(2, 1, false, 1) }
     else { if (p.taps == 9) TC2_GO(1, 9, false, 2) else TC2_GO(1, 1, false, 3) }
 #undef TC2_GO

@@ -234,6 +234,38 @@ extern "C" int ddpm_pack_weights(const float* w, int Cout, int Cin, int KH, int 
     return 0;
 }
 
+// Phase weights of conv3x3(nearest_upsample_x2(x)) evaluated on the low-resolution x (see DDPM_CONV_UP2X_PHASE):
+// rows (py, ty) -> which ky of the 3x3 filter land on low-res row y + ty + py - 1.
+template <typename T>
+__global__ void pack_up2x_kernel(const float* __restrict__ w, int Cout, int Cin, T* out) {
+    const int64_t total = (int64_t)4 * Cout * 4 * Cin;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int ci = (int)(i % Cin); int64_t r = i / Cin;
+        int t = (int)(r % 4); r /= 4;
+        int co = (int)(r % Cout); int ph = (int)(r / Cout);
+        const int py = ph >> 1, px = ph & 1, ty = t >> 1, tx = t & 1;
+        // S(0,0)={0}, S(0,1)={1,2}, S(1,0)={0,1}, S(1,1)={2}
+        const int ky0 = (py == 0) ? (ty == 0 ? 0 : 1) : (ty == 0 ? 0 : 2), ky1 = (py == 0) ? (ty == 0 ? 0 : 2) : (ty == 0 ? 1 : 2);
+        const int kx0 = (px == 0) ? (tx == 0 ? 0 : 1) : (tx == 0 ? 0 : 2), kx1 = (px == 0) ? (tx == 0 ? 0 : 2) : (tx == 0 ? 1 : 2);
+        const float* wk = w + ((int64_t)co * Cin + ci) * 9;
+        float v = 0.f;
+        for (int ky = ky0; ky <= ky1; ++ky)
+            for (int kx = kx0; kx <= kx1; ++kx) v += wk[ky * 3 + kx];
+        stf<T>(out + i, v);
+    }
+}
+extern "C" int ddpm_pack_weights_up2x(const float* w, int Cout, int Cin, void* out, int dtype, void* stream) {
+    if (!w || !out || Cout <= 0 || Cin <= 0) return DDPM_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t total = (int64_t)16 * Cout * Cin;
+    int grid = (int)((total + 255) / 256); if (grid > 148 * 8) grid = 148 * 8;
+    if (dtype == DDPM_F32) pack_up2x_kernel<float><<<grid, 256, 0, st>>>(w, Cout, Cin, (float*)out);
+    else if (dtype == DDPM_BF16) pack_up2x_kernel<bf16><<<grid, 256, 0, st>>>(w, Cout, Cin, (bf16*)out);
+    else return DDPM_E_ARG;
+    LAUNCH_OK();
+    return 0;
+}
+
 // All packed copies in ONE launch (after the optimiser step every weight is stale at once; 76 per-weight launches
 // of a few microseconds each were 0.4 ms of a 16 ms step).  `entries` lives in device memory.
 // Tiles of 32 output x 32 input channels (x all taps) go through shared memory: the OIHW rows are read fully coalesced

@@ -161,6 +161,12 @@ int ddpm_colsum(const ddpm_tensor* dy, int dtype, float* out_nc, float* dbias, v
  * nn.Linear as a 1x1 conv on H=W=1 (attention.py:30,32; unet_backbone.py:27). */
 #define DDPM_CONV_NORMAL 0
 #define DDPM_CONV_TRANSPOSED 1 /* gather for the data-gradient of a strided conv */
+#define DDPM_CONV_UP2X_PHASE 2 /* one output phase of `conv3x3(nearest_upsample_x2(in))` (unet_backbone.py:63-64) computed straight
+                                * from the LOW-resolution input: out[n, 2y+py, 2x+px] = bias + sum over a 2x2 neighbourhood of
+                                * in[n, y+ty+py-1, x+tx+px-1] with the phase's pre-summed weights (ddpm_pack_weights_up2x).
+                                * `in` is [N,H,W,Cin], `out` the [N,2H,2W,Cout] view; KH = KW = 2, stride 1, up_phase = 2*py+px.
+                                * Four calls cover the output: 16 instead of 36 multiply-adds per low-resolution pixel pair
+                                * and the up-sampled tensor is never materialised.  Tensor-core path (bf16) only. */
 #define DDPM_EPI_ACCUM 1       /* out += result (in place; gradient fan-in, residual) */
 #define DDPM_EPI_DSILU 2       /* result *= silu'(z[n,c])  (time path backward) */
 typedef struct {
@@ -184,6 +190,7 @@ typedef struct {
      * (stride-1 main conv); w2 is packed [Cout][1][Cin2].  in2.ptr == NULL: none. */
     ddpm_tensor in2;
     const void* w2;
+    int32_t up_phase;      /* DDPM_CONV_UP2X_PHASE: 2*py + px in 0..3 (ignored otherwise) */
 } ddpm_conv_args;
 int ddpm_conv(const ddpm_conv_args* a, void* stream);
 /* test / tuning hooks: force the CUDA-core kernels; choose the tcgen05 operand layout
@@ -235,6 +242,11 @@ int64_t ddpm_wgrad_workspace_bytes(const ddpm_wgrad_args* a);
  * (dgrad); padded rows/columns are zero.  cin_pad / cout_pad <= 0 mean "no padding". */
 int ddpm_pack_weights(const float* w, int Cout, int Cin, int KH, int KW, void* w_fwd, void* w_dgrad,
                       int dtype, int cin_pad, int cout_pad, void* stream);
+
+/* Phase weights of the folded `nearest x2 up-sample + conv3x3` (DDPM_CONV_UP2X_PHASE): out[ph][co][t][ci] (ph = 2*py+px,
+ * t = 2*ty+tx) = sum of w[co][ci][ky][kx] over ky in S(py,ty), kx in S(px,tx) with S(0,0)={0}, S(0,1)={1,2}, S(1,0)={0,1},
+ * S(1,1)={2} -- summed in fp32, then rounded to `dtype`.  w is fp32 OIHW [Cout][Cin][3][3] (unet_backbone.py:60). */
+int ddpm_pack_weights_up2x(const float* w, int Cout, int Cin, void* out, int dtype, void* stream);
 
 /* the same for many weights in one launch; `entries_dev` is an array in DEVICE memory */
 typedef struct {

@@ -391,3 +391,45 @@ def test_groupnorm_slab_kernels_match_streaming_kernels_and_aten(shape, mode):
     xr = x.interior().float().permute(0, 3, 1, 2)
     ref = F.group_norm(xr, 32, gn.weight, gn.bias, eps=1e-6).permute(0, 2, 3, 1)
     assert rel(b["y_plain"], ref) < 6e-3
+
+
+@pytest.mark.parametrize("case", [(2, 32, 32, 8, 8), (3, 192, 192, 16, 16), (2, 192, 192, 32, 32), (1, 128, 128, 128, 128), (5, 64, 64, 4, 4)])
+def test_upsample_folded_into_the_conv_gather(case, monkeypatch):
+    """Upsample = nearest x2 + conv3x3 (unet_backbone.py:56-64) on the tensor-core path: four 2x2-tap phase convolutions
+    of the LOW-resolution input with pre-summed weights (DDPM_CONV_UP2X_PHASE) against (i) ATen fp32 on the bf16-rounded
+    input and (ii) the materialising path (up-sample kernel + 3x3 convolution).  The phase weights are summed in fp32 and
+    rounded once, the reference rounds each of the nine weights: bf16 tolerance 1e-2."""
+    from ddpm_diffusion_model_b200 import _lib, engine
+    from ddpm_diffusion_model_b200.model.unet_backbone import Upsample
+    import torch.nn.functional as F
+    N, Ci, Co, H, W = case
+    torch.manual_seed(9)
+    mod = Upsample(Ci).to(dev())
+    assert mod.conv.out_channels == Co
+    E = engine.Exec(dev(), _lib.BF16, False, False)
+    x = E.act(N, H, W, Ci); x.interior().normal_()
+    wide = E.act(N, 2 * H, 2 * W, Co + 32)                                      # the real target is a slice of the concat buffer
+    wide.interior().zero_()                                                     # (pooled buffers come back with old interiors)
+    tgt = wide.slice(16, Co)
+    n0 = _lib.launch_count(reset=True)
+    out, saved = engine.up_fwd(E, mod, x, tgt)
+    torch.cuda.synchronize()
+    assert _lib.launch_count(reset=True) == 5                                   # the weight pack (first use) + four phase launches
+    assert saved is None
+    monkeypatch.setenv("DDPM_B200_FOLD_UPSAMPLE", "0")
+    out2, _ = engine.up_fwd(E, mod, x, None)
+    torch.cuda.synchronize()
+    xr = x.interior().float().permute(0, 3, 1, 2)
+    ref = F.conv2d(F.interpolate(xr, scale_factor=2, mode="nearest"), mod.conv.weight.detach().bfloat16().float(), mod.conv.bias, padding=1)
+    got = out.interior().float().permute(0, 3, 1, 2)
+    assert rel(got, ref) < 1e-2, rel(got, ref)
+    assert rel(got, out2.interior().float().permute(0, 3, 1, 2)) < 1e-2
+    # neighbours of the slice and the halo are untouched
+    full = wide.buf.t.float()
+    assert float(full[..., :16].abs().max()) == 0 and float(full[..., 16 + Co:].abs().max()) == 0
+    assert float(full[:, 0].abs().max() + full[:, -1].abs().max() + full[:, :, 0].abs().max() + full[:, :, -1].abs().max()) == 0
+    # with gradients the materialising path runs (backward needs the up-sampled tensor anyway; measured: no gain from folding)
+    Eg = engine.Exec(dev(), _lib.BF16, True, True)
+    monkeypatch.setenv("DDPM_B200_FOLD_UPSAMPLE", "1")
+    out3, u = engine.up_fwd(Eg, mod, x, None)
+    assert u is not None and rel(out3.interior().float(), out.interior().float()) < 1e-2
