@@ -1179,6 +1179,164 @@ __global__ void __launch_bounds__(TC_THREADS) wgrad_tc_kernel(const __grid_const
     }
 }
 
+// ================================================================================================
+// Pair variant of the weight gradient (cta_group::2): the two output-channel tiles of a layer with Cout in (128, 256]
+// (or each pair of tiles for wider layers) are computed by the two CTAs of a cluster as ONE M = 256 MMA.
+//
+// Why (ncu, profiles/r2_ncu_prof_wgrad_192_32.txt): the single-CTA kernel receives 966 MB through the L2->SM crossbar
+// for 114 MB of tensors at 192->192@32 -- 39 B/clk per SM, 92 % of the ~42 B/clk/SM the fabric sustains -- with the
+// tensor pipe 65 % active and the shared-memory banks only 38 % (reads) + 16 % (writes) busy: it is bound by operand
+// INGEST per SM, not by shared-memory bandwidth (round 1's reading).  Per 64-pixel stage a CTA took in 16 KB of dY and
+// 18.4 KB of activation patch.  Here each CTA still stages its own dY tile (its 128 output channels = its half of M)
+// but only HALF of the patch channels (N/2); both tensor cores read both halves -> 25.2 KB per stage and CTA (-27 %),
+// and one more pipeline stage fits.  Barrier protocol as in conv_tc2_kernel: full[s] lives in the leader and collects
+// the bytes of both CTAs, empty[s] / acc_full are tcgen05.commit multicasts to both.
+// The epilogue, the workspace layout and the reduce kernel are those of the single-CTA kernel.
+// ================================================================================================
+#define WG2_STAGES 6
+__global__ void __launch_bounds__(TC_THREADS) wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tmY,
+                                                                const __grid_constant__ CUtensorMap tmA, WgTcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* ones = smem + (size_t)WG2_STAGES * p.stage_bytes;           // [16 px][64 ch] of bf16 1.0 (2 KB, 1024-aligned)
+    uint64_t* full = (uint64_t*)(ones + 2048);
+    uint64_t* empty = full + WG2_STAGES;
+    uint64_t* acc_full = empty + WG2_STAGES;
+    uint32_t* tmem_slot = (uint32_t*)(acc_full + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();                    // cluster (2,1,1): rank = blockIdx.x & 1 = which tile of the pair
+    const bool leader = rank == 0;
+    const int split = blockIdx.z, mtile = blockIdx.x;            // (grid = m_tiles x groups x splits: the pair sits on x like conv_tc2's)
+    const int ky = (int)blockIdx.y / p.n_tiles;
+    const int ntile = (int)blockIdx.y - ky * p.n_tiles;
+    const int grp = ky * p.n_tiles + ntile;
+    const bool do_bias = p.ws_bias != nullptr;
+    const int ngrp = gridDim.y;
+    const int m0 = mtile * 128, n0 = ntile * p.NT + (int)rank * (p.NT / 2);
+    const int s_beg = split * p.stages_per_cta;
+    const int s_end = min(p.stages_total, s_beg + p.stages_per_cta);
+    const int nst = max(0, s_end - s_beg);
+    const int y_bytes = 2 * WG_KQ * 128;                 // two 64-channel blocks of dY
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        for (int i = 0; i < WG2_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc2(tmem_slot, (uint32_t)p.tmem_cols);
+    if (do_bias && warp >= 2) {
+        for (int i = threadIdx.x - 64; i < 2048 / 4; i += TC_THREADS - 64) reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;
+        fence_proxy_async();
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                  // the peer's barriers are initialised before anyone signals them
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t bias_col = (uint32_t)(p.ntap * p.NT);
+    pdl_enter();
+
+    if (warp == 0) {
+        // ===================================================================== TMA producer (both CTAs)
+        if (lane == 0) {
+            for (int i = 0; i < nst; ++i) {
+                const int s = i % WG2_STAGES; const uint32_t ph = (i / WG2_STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                uint8_t* dst = smem + (size_t)s * p.stage_bytes;
+                const uint32_t fbar = mapa_u32(smem_u32(&full[s]), 0);
+                if (leader) mbar_expect_tx(&full[s], (uint32_t)(2 * (y_bytes + WG_ROWS * 128)));
+                const int Q = (s_beg + i) * WG_KQ;
+                tma2_load_2d(dst, &tmY, fbar, m0, Q);
+                tma2_load_2d(dst + WG_KQ * 128, &tmY, fbar, m0 + 64, Q);
+                const int rowA = p.ntap == 3 ? Q + (ky - 1) * p.Wp - 1 : Q;
+                tma2_load_2d(dst + y_bytes, &tmA, fbar, n0, rowA);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================================== MMA issuer (leader CTA only)
+        if (leader) {
+            const bool el = elect_one();
+            // a_major = b_major = MN (bits 15, 16); M = 256 over the pair; N = NT (each CTA holds NT/2 patch channels)
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                                   ((uint32_t)(p.NT >> 3) << 17) | ((256u >> 4) << 24);
+            const uint32_t hi = desc_hi(1024u, 2u);                      // SBO 1024 B, SWIZZLE_128B
+            const uint32_t y_lo0 = desc_lo(smem_u32(smem), (uint32_t)(WG_KQ * 128));
+            const uint32_t a_lo0 = desc_lo(smem_u32(smem) + (uint32_t)y_bytes, (uint32_t)(WG_ROWS * 128));
+            const uint32_t stage16 = (uint32_t)(p.stage_bytes >> 4);
+            const bool three = p.ntap == 3;
+            const uint32_t idesc_b = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((16u >> 3) << 17) | ((256u >> 4) << 24);
+            const uint64_t ones_desc = desc_pack(desc_lo(smem_u32(ones), 2048u), hi);
+            auto run = [&](auto with_bias, auto with_three) {
+                constexpr bool BIAS = decltype(with_bias)::value, THREE = decltype(with_three)::value;
+                uint32_t acc = 0, accb = 0;
+                int kmod = ((s_beg * (WG_KQ / 16)) % ngrp);
+                for (int i = 0; i < nst; ++i) {
+                    const uint32_t s = (uint32_t)(i % WG2_STAGES); const uint32_t ph = (i / WG2_STAGES) & 1;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t y_lo = y_lo0 + s * stage16, a_lo = a_lo0 + s * stage16;
+#pragma unroll
+                    for (int ks = 0; ks < WG_KQ / 16; ++ks) {
+                        const uint64_t ydesc = desc_pack(y_lo + (uint32_t)(ks * 16 * 128 / 16), hi);
+                        if (el) umma2_bf16(tmem_base, ydesc, desc_pack(a_lo + (uint32_t)((ks * 16) * 8), hi), idesc, ks == 0 ? acc : 1u);
+                        if (THREE && el) {
+                            umma2_bf16(tmem_base + (uint32_t)p.NT, ydesc, desc_pack(a_lo + (uint32_t)((ks * 16 + 1) * 8), hi), idesc, ks == 0 ? acc : 1u);
+                            umma2_bf16(tmem_base + (uint32_t)(2 * p.NT), ydesc, desc_pack(a_lo + (uint32_t)((ks * 16 + 2) * 8), hi), idesc, ks == 0 ? acc : 1u);
+                        }
+                        if (BIAS) {
+                            if (kmod == grp) { if (el) umma2_bf16(tmem_base + bias_col, ydesc, ones_desc, idesc_b, accb); accb = 1; }
+                            if (++kmod == ngrp) kmod = 0;
+                        }
+                    }
+                    acc = 1;
+                    if (el) umma2_commit_mc(&empty[s]);
+                    __syncwarp();
+                }
+            };
+            if (do_bias) { if (three) run(std::true_type{}, std::true_type{}); else run(std::true_type{}, std::false_type{}); }
+            else { if (three) run(std::false_type{}, std::true_type{}); else run(std::false_type{}, std::false_type{}); }
+            if (el) umma2_commit_mc(acc_full);
+            __syncwarp();
+        }
+    } else {
+        // ===================================================================== epilogue (both CTAs: own 128 output channels)
+        const int qd = warp & 3;
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        const int cols = p.ntap * p.NT;
+        float* dst = p.ws + ((((size_t)split * p.m_tiles + mtile) * gridDim.y + grp) * 128 + qd * 32 + lane) * cols;
+#pragma unroll 1
+        for (int c0 = 0; c0 < cols; c0 += 16) {
+            uint32_t r[16];
+            if (nst > 0) {
+                tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)c0, r);
+                tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) r[i] = 0u;
+            }
+#pragma unroll
+            for (int i = 0; i < 16; i += 4)
+                *reinterpret_cast<uint4*>(dst + c0 + i) = make_uint4(r[i], r[i + 1], r[i + 2], r[i + 3]);
+        }
+        if (do_bias) {
+            uint32_t r[16];
+            const int k0 = s_beg * (WG_KQ / 16), k1 = s_end * (WG_KQ / 16);
+            const int first = k0 + ((grp - k0 % ngrp) % ngrp + ngrp) % ngrp;
+            if (nst > 0 && first < k1) { tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + bias_col, r); tmem_ld_wait(); }
+            else r[0] = 0u;
+            p.ws_bias[(((size_t)split * ngrp + grp) * p.m_tiles + mtile) * 128 + qd * 32 + lane] = __uint_as_float(r[0]);
+        }
+        tc_fence_before();
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                  // nobody exits (or frees TMEM) while the pair is still working
+    if (warp == 1) { tc_fence_after(); tmem_dealloc2(tmem_base, (uint32_t)p.tmem_cols); }
+}
+
 // dw[co][ci][ky][kx] += sum_split ws[split][mtile][ky*n_tiles+ntile][co%128][kx*NT + ci%NT]
 __device__ __forceinline__ void wgrad_reduce_body(const float* __restrict__ ws, float* __restrict__ dw, int splits, const WgTcParams& p,
                                                   int gtid, int gthreads) {
@@ -1261,6 +1419,15 @@ static int wg_max_clusters(size_t smem) {
     return n;
 }
 
+static int wg_pair(const WgTcParams& p) {
+    // the pair kernel: an even number of 128-row output-channel tiles (Cout in (128,256], (384,512], ...); bit 10 of the
+    // experiment flags turns it off (A/B against the single-CTA kernel)
+    // Measured (profiles/r2_kbench_wgrad_pair_vs_single.txt): -9 % on the large Cout = 192 layers, +5 % on 384->192 @ 16 / 8
+    // (four ci tiles x few pixels: the halved split count costs more than the smaller patch saves) -> small problems with
+    // many ci tiles stay on the single-CTA kernel.
+    if (p.n_tiles > 2 && p.stages_total < 1500) return 0;
+    return (p.m_tiles % 2 == 0) && !(g_tc_exp & 1024) && !p.cl3 && p.NT % 16 == 0;
+}
 static void wg_plan(const ddpm_wgrad_args* a, WgTcParams* p, int* splits) {
     p->Cin = a->act.C; p->Cout = a->dy.C; p->NT = wg_pick_nt(p->Cin);
     p->ntap = a->KH == 3 ? 3 : 1;
@@ -1289,6 +1456,7 @@ static void wg_plan(const ddpm_wgrad_args* a, WgTcParams* p, int* splits) {
     if (sp < 1) sp = 1;
     p->stages_per_cta = (p->stages_total + sp - 1) / sp;
     *splits = (p->stages_total + p->stages_per_cta - 1) / p->stages_per_cta;
+    if (wg_pair(*p)) p->stage_bytes = 2 * WG_KQ * 128 + WG_ROWS * 128;      // own dY tile + HALF of the patch channels (one 64-channel box)
 }
 
 extern "C" int64_t ddpm_wgrad_workspace_bytes(const ddpm_wgrad_args* a) {
@@ -1329,9 +1497,32 @@ int wgrad_tc_launch(const ddpm_wgrad_args* a, cudaStream_t st) {
         uint32_t b[2] = {64, WG_ROWS};
         if (encode(&tmA, a->act.ptr, 2, d, s, b, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
     }
+    dim3 grid(splits, p.ntap * p.n_tiles, p.m_tiles);
+    if (wg_pair(p)) {
+        const size_t smem2 = (size_t)WG2_STAGES * p.stage_bytes + 2048 + 8 * (2 * WG2_STAGES + 1) + 16 + 1024;
+        static size_t configured2 = 0;
+        if (smem2 > configured2) {
+            CUDA_TRY(cudaFuncSetAttribute(wgrad_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            configured2 = smem2;
+        }
+        p.dw = nullptr;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(p.m_tiles, p.ntap * p.n_tiles, splits); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem2; cfg.stream = st;
+        cudaLaunchAttribute at[2]; unsigned nat = 1;
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        pdl_attr(at, &nat);
+        cfg.attrs = at; cfg.numAttrs = nat;
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, wgrad_tc2_kernel, tmY, tmA, p));
+        LAUNCH_OK();
+        int total = p.CoutV * p.ntap * p.ntap * p.CinV;
+        int rg = (total + 255) / 256; if (rg > 148 * 8) rg = 148 * 8;
+        CUDA_TRY(launch_pdl(wgrad_reduce_kernel, dim3(rg), dim3(256), 0, st, (const float*)p.ws, a->dw, splits, p));
+        LAUNCH_OK();
+        return 0;
+    }
     size_t smem = wg_smem_bytes(p);
     rc = wg_set_smem(smem); if (rc) return rc;
-    dim3 grid(splits, p.ntap * p.n_tiles, p.m_tiles);
     // In-kernel split-K reduction behind a cooperative grid barrier: measured SLOWER on B200 (a cooperative launch costs
     // ~50 us: 96->96@64 100 -> 153 us), so it stays an experiment (bit 8 of the flags); default = separate reduce kernel.
     const bool fused = (g_tc_exp & 256) && !p.cl3 && (int)(grid.x * grid.y * grid.z) <= sm_count();

@@ -83,7 +83,15 @@ class DeviceLoader:
         return order[rank:per * world:world]
 
     def _order(self) -> torch.Tensor:
-        return self.shard_order(self.epoch_order(self.N, self.shuffle, self.generator), self.rank, self.world)
+        order = self.epoch_order(self.N, self.shuffle, self.generator)
+        if self.world > 1 and self.shuffle and self.generator is None:
+            # every rank would otherwise draw its own permutation from its own global RNG and the rank::world slices
+            # would overlap / miss samples: rank 0's permutation is the epoch's permutation for everybody
+            import torch.distributed as dist
+            o = order.to(self.device)
+            dist.broadcast(o, src=0)
+            order = o.cpu()
+        return self.shard_order(order, self.rank, self.world)
 
     def __len__(self) -> int:
         n = self.N // self.world if self.world > 1 else self.N

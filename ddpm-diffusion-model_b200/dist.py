@@ -67,10 +67,16 @@ class GradSync:
         self.g = flat_grad
         self.group = group
         self.spans = module_spans
+        # Measured on 8 B200 (profiles/r2_timeline_dp8*.txt): with plain 16 MB buckets the third bucket cannot start before
+        # the first encoder level is done, i.e. at the very end of backward -- 181 us of exposed all-reduce.  Cutting the
+        # first 12 MB into 2 MB buckets halves the exposed wait (100 us) but the nine NCCL kernels steal more SM time from
+        # the overlapped backward than that saves (12.59 vs 12.50 ms per step).  One boundary at 4 MB keeps four launches:
+        # [4 MB, ...) goes out while the first encoder level's backward (~1 ms) is still running, only [0, 4 MB)
+        # (time MLP, in/out convolutions, first encoder level) is exposed.
         if tail_bytes is None:
-            tail_bytes = int(os.environ.get("DDPM_B200_DP_TAIL_MB", "12")) << 20
+            tail_bytes = int(os.environ.get("DDPM_B200_DP_TAIL_MB", "4")) << 20
         if tail_bucket_bytes is None:
-            tail_bucket_bytes = int(os.environ.get("DDPM_B200_DP_TAIL_BUCKET_KB", "2048")) << 10
+            tail_bucket_bytes = int(os.environ.get("DDPM_B200_DP_TAIL_BUCKET_KB", "4096")) << 10
         self.buckets = make_buckets(flat_grad.numel(), max(1, bucket_bytes // 4), tail_bytes // 4, max(1, tail_bucket_bytes // 4))
         self.cuda = flat_grad.is_cuda
         self.comm = torch.cuda.Stream(flat_grad.device) if self.cuda else None
