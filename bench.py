@@ -487,6 +487,9 @@ GUARD = None
 
 def main():
     global GUARD
+    if os.environ.get("DDPM_BENCH_WATCHDOG"):            # diagnostics: dump every thread's Python stack if the run stalls
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["DDPM_BENCH_WATCHDOG"]), repeat=True, file=sys.stderr)
     GUARD = _StdoutGuard()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)

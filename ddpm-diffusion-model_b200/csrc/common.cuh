@@ -31,7 +31,7 @@ static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b)
 // first access to global memory (it returns once every prerequisite grid has completed and flushed), and call
 // pdl_trigger() to let the NEXT kernel of the stream start its own prologue.  Every kernel that is ever launched
 // this way waits before it exits, so completion stays transitive along the stream.
-extern int g_ddpm_pdl;           // 1 (default; env DDPM_B200_PDL=0 or ddpm_set_pdl(0) turns it off)
+extern int g_ddpm_pdl;           // 0 (default since round 2; env DDPM_B200_PDL=1 or ddpm_set_pdl(1) turns it on)
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_enter() { pdl_wait(); pdl_trigger(); }

@@ -1421,12 +1421,15 @@ static int wg_max_clusters(size_t smem) {
 
 static int wg_pair(const WgTcParams& p) {
     // the pair kernel: an even number of 128-row output-channel tiles (Cout in (128,256], (384,512], ...); bit 10 of the
-    // experiment flags turns it off (A/B against the single-CTA kernel)
+    // experiment flags turns it off (A/B against the single-CTA kernel).  It is never given the programmatic-dependent-launch
+    // attribute: launched that way on the MAIN stream it dead-locked the GPU in 4 of 10 CelebA256 bench runs (0 of 6 without
+    // the attribute, 0 of 4 with the single-CTA kernel; mechanism not found -- DESIGN.md section 4.4).
+    if (g_tc_exp & 1024) return 0;
     // Measured (profiles/r2_kbench_wgrad_pair_vs_single.txt): -9 % on the large Cout = 192 layers, +5 % on 384->192 @ 16 / 8
     // (four ci tiles x few pixels: the halved split count costs more than the smaller patch saves) -> small problems with
     // many ci tiles stay on the single-CTA kernel.
     if (p.n_tiles > 2 && p.stages_total < 1500) return 0;
-    return (p.m_tiles % 2 == 0) && !(g_tc_exp & 1024) && !p.cl3 && p.NT % 16 == 0;
+    return (p.m_tiles % 2 == 0) && !p.cl3 && p.NT % 16 == 0;
 }
 static void wg_plan(const ddpm_wgrad_args* a, WgTcParams* p, int* splits) {
     p->Cin = a->act.C; p->Cout = a->dy.C; p->NT = wg_pick_nt(p->Cin);
@@ -1511,7 +1514,7 @@ int wgrad_tc_launch(const ddpm_wgrad_args* a, cudaStream_t st) {
         cudaLaunchAttribute at[2]; unsigned nat = 1;
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        pdl_attr(at, &nat);
+        if (g_tc_exp & 2048) pdl_attr(at, &nat);      // experiments only (bit 11): see wg_pair()
         cfg.attrs = at; cfg.numAttrs = nat;
         CUDA_TRY(cudaLaunchKernelEx(&cfg, wgrad_tc2_kernel, tmY, tmA, p));
         LAUNCH_OK();

@@ -11,7 +11,11 @@
 #include <math.h>
 
 int64_t g_ddpm_launches = 0;
-static int pdl_default() { const char* e = getenv("DDPM_B200_PDL"); return !(e && e[0] == '0'); }
+// Programmatic dependent launch is OFF by default since round 2 (DDPM_B200_PDL=1 / ddpm_set_pdl(1) turn it on): measured in one
+// call it is neutral at 64 px (12.10 vs 12.12 ms per train step, DDIM-100 390 vs 392 samples/s) and COSTS 5 % of the CelebA256
+// train step (445 vs 467 img/s) and 25 % of a 256-px sampler evaluation (15.1 vs 12.1 ms) -- early-launched dependents sit on SM
+// resources next to the long-running kernels -- and with it the opt-in pair wgrad kernel dead-locked.
+static int pdl_default() { const char* e = getenv("DDPM_B200_PDL"); return (e && e[0] == '1') ? 1 : 0; }
 int g_ddpm_pdl = pdl_default();
 extern "C" int ddpm_set_pdl(int on) { g_ddpm_pdl = on ? 1 : 0; return 0; }
 extern "C" int ddpm_abi_struct_sizes(int32_t* out, int n) {

@@ -111,10 +111,23 @@ WGRAD = [  # N, Cin, Cout, H, W, k
 ]
 
 
+@pytest.mark.parametrize("pair", [0, 1])
 @pytest.mark.parametrize("case", WGRAD)
-def test_wgrad_tc_matches_simt(mods, case):
+def test_wgrad_tc_matches_simt(mods, case, pair):
+    """`pair` = 1: the cta_group::2 pair kernel (two output-channel tiles as one M = 256 MMA) where the layer has an even number
+    of 128-row tiles; `pair` = 0 forces the single-CTA kernel (experiment bit 10)."""
     _lib, engine = mods
     N, Ci, Co, H, W, k = case
+    if pair and ((Co + 127) // 128) % 2:
+        pytest.skip("odd number of output-channel tiles: the single-CTA kernel runs either way")
+    _lib.lib.ddpm_set_tc_mode(1 | ((0 if pair else 1024) << 4), 0)
+    try:
+        _wgrad_case(_lib, engine, N, Ci, Co, H, W, k)
+    finally:
+        _lib.lib.ddpm_set_tc_mode(1, 0)
+
+
+def _wgrad_case(_lib, engine, N, Ci, Co, H, W, k):
     torch.manual_seed(2)
     E = engine.Exec(dev(), _lib.BF16, True, True)
     x = E.act(N, H, W, Ci); x.interior().normal_()

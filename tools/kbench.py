@@ -21,7 +21,7 @@ ap.add_argument("--json", default=None)
 ap.add_argument("--epi", action="store_true", help="conv: also time with bias + time-bias + residual epilogue")
 ap.add_argument("--v1", action="store_true", help="conv: also time the first-generation kernel")
 ap.add_argument("--gnshape", default=None, help="restrict gn to one 'C,H'")
-ap.add_argument("--tcexp", type=int, default=0, help="experiment flags for the whole run (ddpm_set_tc_mode(1 | flags << 4)), e.g. 512 = wgrad with (1,3,1) clusters + dY multicast")
+ap.add_argument("--tcexp", type=int, default=0, help="experiment flags for the whole run (ddpm_set_tc_mode(1 | flags << 4)), e.g. 512 = wgrad with (1,3,1) clusters + dY multicast, 1024 = single-CTA wgrad kernel instead of the pair kernel, 2048 = pair kernel with the PDL attribute")
 ap.add_argument("--gnslab", default="1", help="gn: comma list of ddpm_set_gn_slab modes to time (0 streaming, 1 slab, 2 slab without 16-CTA clusters)")
 ap.add_argument("--shape", default=None, help="restrict conv/wgrad to one 'Cin,Cout,H' (for ncu)")
 args = ap.parse_args()

@@ -14,13 +14,20 @@ from ddpm_diffusion_model_b200.training_loops.train_one_epoch import train_one_e
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+CFG = sys.argv[3] if len(sys.argv) > 3 else "low64"          # or celeba256 (B = 32)
 dev = torch.device("cuda", 0)
 torch.manual_seed(0)
-model = build_unet_64x64(**LOW_GPU).to(dev)
-diff = Diffusion(T=1000, img_size=64).to(dev)
+if CFG == "celeba256":
+    from ddpm_diffusion_model_b200.model.unet_backbone import UNetDenoiser
+    model = UNetDenoiser(3, 128, (1, 1, 2, 2, 4), 2, {16}, 512, 0.1, 4, 64, 256).to(dev)
+    IMG = 256
+else:
+    model = build_unet_64x64(**LOW_GPU).to(dev)
+    IMG = 64
+diff = Diffusion(T=1000, img_size=IMG).to(dev)
 opt = torch.optim.AdamW(model.parameters(), lr=2e-4)
 ema = EMA(model, decay=0.9995); scaler = make_grad_scaler("cuda", True)
-x = torch.empty(B, 3, 64, 64, device=dev).uniform_(-1, 1); y = torch.zeros(B)
+x = torch.empty(B, 3, IMG, IMG, device=dev).uniform_(-1, 1); y = torch.zeros(B)
 step = lambda: train_one_epoch(model, diff, [(x, y)], opt, scaler=scaler, ema=ema, device="cuda:0", grad_clip=1.0)
 epoch = lambda: train_one_epoch(model, diff, [(x, y)] * K, opt, scaler=scaler, ema=ema, device="cuda:0", grad_clip=1.0)
 for _ in range(4):
