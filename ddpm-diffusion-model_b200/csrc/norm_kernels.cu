@@ -969,11 +969,17 @@ static int gn_max_cluster() {              // experiment: DDPM_B200_GN_CS16=1 al
     if (v == 0) { const char* e = getenv("DDPM_B200_GN_CS16"); v = (e && e[0] == '1') ? 16 : 8; }
     return v;
 }
-static int gn_cluster_size(int HW, int cvs) {
+static int gn_cluster_size(int HW, int cvs, int N = 1 << 30) {
     const int64_t packets = (int64_t)HW * cvs;
     int cs = 1;
     while (cs < 8 && packets / (cs * NT) >= 24) cs <<= 1;
     if (cs == 8 && gn_max_cluster() == 16 && packets / (16 * NT) >= 12) cs = 16;
+    // Very few large images (fewer CTAs than SMs with clusters of 8): clusters of 16 (non-portable size) double the number of
+    // CTAs per image -- 256-px sampling at B = 16: 12.3 -> 11.5 ms per evaluation; at B = 32 (256 CTAs already) it measured
+    // 1.4 % SLOWER, hence the N * 8 <= 148 bound.  DDPM_B200_GN_CS16=0 forbids it (A/B).
+    static int allow16 = -1;
+    if (allow16 < 0) { const char* e = getenv("DDPM_B200_GN_CS16"); allow16 = !(e && e[0] == '0'); }
+    if (cs == 8 && allow16 && (int64_t)N * 8 <= 148 && packets / (16 * NT) >= 24) cs = 16;
     return cs;
 }
 static int log2_exact(int v) { int s = 0; while ((1 << s) < v) ++s; return (1 << s) == v ? s : -1; }
@@ -1028,7 +1034,7 @@ static int gn_fwd_dispatch(GnP& p, const ddpm_tensor* x, const ddpm_tensor* out,
     const int HW = x->H * x->W, C = x->C, G = p.G;
     const size_t sm0 = sizeof(double) * (2 * C + 2 * G) + sizeof(float) * 2 * G;
 #define GO(T, VEC) { int cvs = C / VEC; if (cvs > NT) return DDPM_E_ARG; \
-        int cs = MODE == 2 ? 1 : gn_cluster_size(HW, cvs); \
+        int cs = MODE == 2 ? 1 : gn_cluster_size(HW, cvs, x->N); \
         if (MODE == 2) { cs = 1; int want = (HW * cvs) / (NT * 16); while (cs < 8 && cs < want) cs <<= 1; } \
         return launch_cluster(gn_fwd_kernel<T, VEC, MODE>, x->N * cs, cs, sm0 + gn_ring_bytes<VEC, 1, GN_PIPE_D_FWD>(), st, p); }
     const bool v8 = vec_ok(x, 8, 2) && (MODE == 1 || vec_ok(out, 8, 2));
@@ -1094,7 +1100,7 @@ static int gn_bwd_impl(const ddpm_tensor* x, int dtype, int groups, const double
     if (cs_nc) CUDA_TRY(cudaMemsetAsync(cs_nc, 0, sizeof(float) * x->N * x->C, st));
     const int HW = x->H * x->W, C = x->C;
     const size_t sm0 = sizeof(double) * 2 * C + sizeof(float) * (2 * C + 4 * groups);
-#define GO(T, VEC) { int cvs = C / VEC; if (cvs > NT) return DDPM_E_ARG; int cs = gn_cluster_size(HW, cvs); \
+#define GO(T, VEC) { int cvs = C / VEC; if (cvs > NT) return DDPM_E_ARG; int cs = gn_cluster_size(HW, cvs, x->N); \
         const size_t sm = sm0 + gn_ring_bytes<VEC, 3>(); \
         if (p.stash) return launch_cluster(gn_bwd_kernel<T, VEC, true>, x->N * cs, cs, sm, st, p); \
         return launch_cluster(gn_bwd_kernel<T, VEC, false>, x->N * cs, cs, sm, st, p); }

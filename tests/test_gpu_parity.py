@@ -210,7 +210,8 @@ def test_conv_epilogues(pkg):
 
 @pytest.mark.parametrize("dt_name", ["f32", "bf16"])
 @pytest.mark.parametrize("shape", [(2, 32, 8, 8), (2, 96, 8, 8), (1, 288, 4, 4), (2, 64, 16, 16), (3, 96, 64, 64),
-                                   (2, 192, 16, 16), (2, 192, 32, 32), (2, 96, 12, 20)])
+                                   (2, 192, 16, 16), (2, 192, 32, 32), (2, 96, 12, 20),
+                                   (2, 128, 128, 128)])       # last: few large images -> clusters of 16 CTAs
 @pytest.mark.parametrize("act", [0, 1])
 def test_groupnorm_fwd_bwd(pkg, shape, act, dt_name):
     _, _lib, engine = pkg
