@@ -8,7 +8,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libddpm_b200.so")
 SOURCES = ["diffusion_kernels.cu", "norm_kernels.cu", "param_kernels.cu", "conv_simt.cu",
-           "conv_tc.cu", "attn_kernels.cu", "abi_conv.cu"]
+           "conv_tc.cu", "attn_kernels.cu", "attn_tc.cu", "abi_conv.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -11,6 +11,7 @@ int wgrad_tc_launch(const ddpm_wgrad_args* a, cudaStream_t st);
 
 static int g_force_simt = 0;
 extern "C" int ddpm_set_force_simt(int v) { g_force_simt = v; return 0; }
+int ddpm_force_simt_flag() { return g_force_simt; }
 
 extern "C" int ddpm_conv(const ddpm_conv_args* a, void* stream) {
     if (!a || !tensor_ok(&a->in) || !tensor_ok(&a->out) || !a->w) return DDPM_E_ARG;

@@ -94,11 +94,16 @@ __global__ void __launch_bounds__(AT) attn_fwd_kernel(TV qkv, TV out, int heads,
     }
 }
 
+int attn_tc_supported(const ddpm_tensor* qkv, const ddpm_tensor* out, int heads, int d, int dtype);      // attn_tc.cu
+int attn_tc_launch(const ddpm_tensor* qkv, const ddpm_tensor* out, int heads, int d, float* lse, cudaStream_t st);
+int ddpm_force_simt_flag();
 extern "C" int ddpm_attn_fwd(const ddpm_tensor* qkv, const ddpm_tensor* out, int heads, int d, float* lse,
                              int dtype, void* stream) {
     if (!tensor_ok(qkv) || !tensor_ok(out) || !lse || heads <= 0 || d <= 0 || d > DMAX) return DDPM_E_ARG;
     if (qkv->C != 3 * heads * d || out->C != heads * d || out->N != qkv->N || out->H != qkv->H || out->W != qkv->W) return DDPM_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
+    // tcgen05 forward for the UNet's shapes (<= 256 tokens, head_dim 32 / 64, bf16); everything else on the CUDA cores
+    if (!ddpm_force_simt_flag() && attn_tc_supported(qkv, out, heads, d, dtype)) return attn_tc_launch(qkv, out, heads, d, lse, st);
     int N = qkv->H * qkv->W;
     dim3 grid(ceil_div(N, 4 * QPW), heads, qkv->N);
     size_t smem = sizeof(float) * (2 * KT * (d + 1) + 4 * d + 4 * KT);

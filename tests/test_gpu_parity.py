@@ -302,7 +302,8 @@ def test_dropout_statistics(pkg):
 
 
 @pytest.mark.parametrize("dt_name", ["f32", "bf16"])
-@pytest.mark.parametrize("cfg", [(2, 8, 8, 2, 16), (1, 16, 16, 4, 32), (2, 8, 8, 1, 64), (1, 12, 12, 2, 8), (1, 32, 32, 2, 32)])
+@pytest.mark.parametrize("cfg", [(2, 8, 8, 2, 16), (1, 16, 16, 4, 32), (2, 8, 8, 1, 64), (1, 12, 12, 2, 8), (1, 32, 32, 2, 32),
+                                 (2, 16, 16, 4, 64), (3, 8, 8, 2, 32)])     # last two: the CelebA256 / low-GPU blocks (tcgen05 forward in bf16)
 def test_attention_fwd_bwd(pkg, cfg, dt_name):
     _, _lib, engine = pkg
     dt = _lib.F32 if dt_name == "f32" else _lib.BF16
