@@ -101,6 +101,7 @@ SIGNATURES = {
     "ddpm_time_proj_bwd": [_vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _vp],
     "ddpm_attn_fwd": [_TP, _TP, _i, _i, _vp, _i, _vp],
     "ddpm_attn_bwd": [_TP, _TP, _TP, _vp, _TP, _i, _i, _vp, _i, _vp],
+    "ddpm_attn_bwd_scratch_floats": [_TP, _TP, _i, _i, _i],
     "ddpm_param_reduce": [_vp, _i64, _vp, _vp],
     "ddpm_param_update": [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, C.POINTER(AdamHyper), _vp],
     "ddpm_scaler_update": [_vp, _vp, _vp, _f, _f, _i, _vp],
@@ -126,7 +127,7 @@ def _load() -> C.CDLL:
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)        # AttributeError if the ABI symbol is missing
         fn.argtypes = argtypes
-        fn.restype = C.c_int64 if name in ("ddpm_launch_count", "ddpm_wgrad_workspace_bytes") else C.c_int
+        fn.restype = C.c_int64 if name in ("ddpm_launch_count", "ddpm_wgrad_workspace_bytes", "ddpm_attn_bwd_scratch_floats") else C.c_int
     # the ctypes mirrors above must have exactly the layouts the library was compiled with (a silent mismatch would
     # corrupt every launch): compare sizeof() struct by struct and refuse to load otherwise
     mine = [("ddpm_tensor", Tensor), ("ddpm_conv_args", ConvArgs), ("ddpm_lin_entry", LinEntry), ("ddpm_wgrad_args", WgradArgs),

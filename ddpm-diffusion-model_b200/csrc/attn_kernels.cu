@@ -287,12 +287,28 @@ __global__ void __launch_bounds__(AT) attn_bwd_kv_kernel(TV qkv, TV dout, TV dqk
     }
 }
 
+int64_t attn_tc_bwd_scratch_floats(const ddpm_tensor* qkv, const ddpm_tensor* out, int heads, int d, int dtype);      // attn_tc.cu
+int attn_tc_bwd_launch(const ddpm_tensor* qkv, const ddpm_tensor* out, const ddpm_tensor* dout, const float* lse,
+                       const ddpm_tensor* dqkv, int heads, int d, float* scratch, cudaStream_t st);
+extern "C" int64_t ddpm_attn_bwd_scratch_floats(const ddpm_tensor* qkv, const ddpm_tensor* out, int heads, int d, int dtype) {
+    if (!tensor_ok(qkv) || !tensor_ok(out) || heads <= 0 || d <= 0) return 0;
+    const int64_t N = (int64_t)qkv->H * qkv->W;
+    if (!ddpm_force_simt_flag()) {
+        const int64_t tc = attn_tc_bwd_scratch_floats(qkv, out, heads, d, dtype);
+        if (tc > 0) return tc;                             // tensor-core backward: D = dO . O per query only
+    }
+    return 2 * (int64_t)qkv->N * heads * N * N;             // CUDA-core backward: P and dS
+}
 extern "C" int ddpm_attn_bwd(const ddpm_tensor* qkv, const ddpm_tensor* out, const ddpm_tensor* dout,
                              const float* lse, const ddpm_tensor* dqkv, int heads, int d, float* scratch,
                              int dtype, void* stream) {
     if (!tensor_ok(qkv) || !tensor_ok(out) || !tensor_ok(dout) || !tensor_ok(dqkv) || !lse || !scratch) return DDPM_E_ARG;
     if (heads <= 0 || d <= 0 || d > DMAX || qkv->C != 3 * heads * d || dqkv->C != qkv->C || out->C != heads * d || dout->C != out->C) return DDPM_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
+    // tcgen05 backward with P recomputed from lse (no N x N scratch) for the UNet's shapes; CUDA cores otherwise
+    if (!ddpm_force_simt_flag() && attn_tc_supported(qkv, out, heads, d, dtype) && attn_tc_supported(dqkv, dout, heads, d, dtype) &&
+        dout->halo == qkv->halo)
+        return attn_tc_bwd_launch(qkv, out, dout, lse, dqkv, heads, d, scratch, st);
     int N = qkv->H * qkv->W;
     float* Pm = scratch; float* dSm = scratch + (size_t)qkv->N * heads * N * N;
     float scale = 1.0f / sqrtf((float)d);

@@ -666,7 +666,9 @@ def attn_bwd(E: Exec, blk, saved, dout: Act, dx: Optional[Act] = None, dx_accum:
     _, wpd = E.wcache.get(E, blk.proj.weight, E.dt, True)
     do = conv(E, dout, wpd, E.act(x.N, x.H, x.W, inner), 1)
     dqkv = E.act(x.N, x.H, x.W, 3 * inner)
-    scratch = E.f32(2, x.N, heads, n_tok, n_tok)
+    # N x N scratch only on the CUDA-core path; the tcgen05 backward recomputes P from lse and needs one float per query
+    need = int(_lib.lib.ddpm_attn_bwd_scratch_floats(C.byref(qkv.desc()), C.byref(o.desc()), heads, d, E.dt))
+    scratch = E.f32(max(need, 1))
     _lib.call("ddpm_attn_bwd", C.byref(qkv.desc()), C.byref(o.desc()), C.byref(do.desc()), lse.data_ptr(),
               C.byref(dqkv.desc()), heads, d, scratch.data_ptr(), E.dt, E.stream)
     wgrad(E, a, dqkv, blk.qkv.weight, 1)

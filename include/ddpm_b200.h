@@ -267,6 +267,10 @@ int ddpm_attn_fwd(const ddpm_tensor* qkv, const ddpm_tensor* out, int heads, int
 int ddpm_attn_bwd(const ddpm_tensor* qkv, const ddpm_tensor* out, const ddpm_tensor* dout,
                   const float* lse, const ddpm_tensor* dqkv, int heads, int d, float* scratch,
                   int dtype, void* stream);
+/* fp32 elements of `scratch` ddpm_attn_bwd needs for this problem: N*N-sized P and dS matrices for the CUDA-core kernels,
+ * one value per (image, head, query) for the tensor-core kernels (bf16, <= 256 tokens, head_dim 32 / 64), which recompute
+ * P from the forward's log-sum-exp. */
+int64_t ddpm_attn_bwd_scratch_floats(const ddpm_tensor* qkv, const ddpm_tensor* out, int heads, int d, int dtype);
 
 /* ---------------- optimiser-side parameter pass -------------------------------------------- */
 /* train_one_epoch.py:94-115 + ema.py:15-23 over flat fp32 arenas.
