@@ -311,6 +311,12 @@ def run_ours(args):
         sec, launches, last, host_s = timed(step_resident, args.steps)
     enqueue_ms = last_enqueue_ms_per_step()           # host loop time per step, excluding the final synchronising loss read
     pool_misses = _engine.POOL.misses - miss0
+    # ... which includes back-pressure once the launch queue is full (the GPU is the bottleneck at this batch).  The host's own
+    # cost per step is what the same loop takes when the GPU is NOT the limit: the same epoch on two-image batches.
+    x_tiny = x_dev[:2].contiguous()
+    train_one_epoch(model, diff, [(x_tiny, y_host[:2])] * 3, opt, **kw)
+    train_one_epoch(model, diff, [(x_tiny, y_host[:2])] * 8, opt, **kw)
+    enqueue_unloaded_ms = last_enqueue_ms_per_step()
     step_e2e(2)
     sec_e2e, _, last_e2e, _ = timed(step_e2e, args.steps)
     trace = last_step_losses()
@@ -366,11 +372,11 @@ def run_ours(args):
         fl, tt, detail = conv_roofline(dev, B, shapes=C256_SHAPES if c256 else None)
         ach = fl / tt / 1e12
         # traffic: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel at the 96->96@64 shape
-        # (B=128), from the committed `ncu --set full` capture profiles/r1_ncu_prof_final_conv_96_96_64.txt
-        # (107.3 MB read = the input tensor once, 61.6 MB written back before the kernel ended; the algorithmic
+        # (B=128), from the committed `ncu --set full` capture profiles/r2_ncu_prof_conv_96_96_64.txt
+        # (107.3 MB read = the input tensor once, 63.9 MB written back before the kernel ended; the algorithmic
         # bytes of that launch are 107 MB in + 107 MB out + 0.17 MB weights)
         roof = {"bound": "tensor", "achieved": ach, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": ach / pk["tf_burst"],
-                "traffic": 168904960 if (B == 128 and not c256) else None, "traffic_shape": "96->96@64, B=128",
+                "traffic": 171145216 if (B == 128 and not c256) else None, "traffic_shape": "96->96@64, B=128",
                 "kernel": "conv_tc2_kernel (tcgen05 cta_group::2 implicit GEMM; 3x3 s1 layers of the %s UNet, count-weighted, B=%d)" % ("CelebA256" if c256 else "low-GPU", B),
                 "peak_source": pk["src"] + " bf16 burst (kernel timed alone)", "per_shape": detail,
                 "step_tensor_frac": (gf_train * 1e9 * world * B * args.steps / sec) / (world * pk["tf_sus"] * 1e12)}
@@ -457,7 +463,7 @@ def run_ours(args):
                                                "gather+ToTensor+Normalize kernel per step)"},
                     "sync_every_step": {"value": world * B / sec_sync, "ms_per_step": sec_sync * 1e3,
                                         "timed": "one train_one_epoch call PER step (host reads the loss after every step)"}},
-            "gpu_launches": launches, "host_enqueue_ms_per_step": enqueue_ms,
+            "gpu_launches": launches, "host_enqueue_ms_per_step": enqueue_ms, "host_enqueue_ms_per_step_unloaded": enqueue_unloaded_ms,
             "clocks": clk.summary(), "roofline": roof, "cpu_baseline": cpu,
             "loss": last[0] if last else None, "pool_misses_in_timed_region": pool_misses, "ddim100": ddim,
             "train_tflops_per_gpu": gf_train * 1e9 * B * args.steps / sec / 1e12,
