@@ -383,6 +383,10 @@ int conv_tc_supported(const ddpm_conv_args* a) {
     if (a->res.ptr && (a->res.halo != 1 || a->res.pitch % 8 || ((uintptr_t)a->res.ptr & 15))) return 0;
     if (pick_nt(out.C) == 0) return 0;
     if (in.W + 2 > 300) return 0;         // patch would not fit the A ring (large images: later round)
+    if (a->gn_ab) {                       // GroupNorm (+SiLU) on the input operand: persistent pair kernel, stride-1 3x3 / 1x1 only
+        if (!g_tc_v2_flag() || g_tc_mode != 1 || up || a->stride != 1 || (a->epi & DDPM_EPI_DSILU)) return 0;
+        if (((uintptr_t)a->gn_ab & 15) || a->gn_act < 0 || a->gn_act > 1) return 0;
+    }
     if (a->in2.ptr) {                     // fused 1x1 second operand: persistent pair kernel, 3x3 stride-1 main conv only
         const ddpm_tensor& i2 = a->in2;
         if (!g_tc_v2_flag() || g_tc_mode != 1 || a->KH != 3 || a->stride != 1 || (a->epi & DDPM_EPI_DSILU)) return 0;
@@ -503,6 +507,28 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     // to drain (ncu: MEMBAR + ERRBAR = 16 % of the stall samples) for no reason
     asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t cluster_addr) {
+    // publishes this warp's shared-memory writes (already made visible to the async proxy by fence.proxy.async) to the
+    // MMA-issuing thread of the pair's leader CTA
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_acq_cluster(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAITC_%=:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONEC_%=;\n\t"
+        "bra WAITC_%=;\n\t"
+        "DONEC_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ uint4 lds128u(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128u(uint32_t a, const uint4& v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 __device__ __forceinline__ void tma2_load_2d(void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(m), "r"(bar_cluster_addr), "r"(c0), "r"(c1) : "memory");
@@ -564,13 +590,26 @@ struct Tc2Params {
     int KCH2;                     // K-chunks of the fused 1x1 second operand (0: none): they follow the 3x3 chunks of every
     int b2_chunk_bytes;           //    item, load their patch through tmA2 / their one-tap weight slab through tmB2 and
                                   //    issue only the centre tap
+    const float* gn_ab;           // GNA kernels: fp32 [N][2][Cin] GroupNorm affine of the input operand (ddpm_conv_args.gn_ab)
+    int gn_act;                   //    1: SiLU after the affine
+    int gn_nimg;                  //    images a CTA's patch can span (rows of the shared-memory coefficient table)
 };
 
 // FUSED2: the 1x1 second operand (ddpm_conv_args.in2).  A template parameter, not a run-time branch: the extra stage kind
 // in the producer and MMA-issue loops cost 3-4 % on EVERY convolution when it was one (A/B of three builds on one box,
 // 96->96@64: 67.9 -> 70.0 us) -- the issue loop is that tight.
-template <int MT, int TAPS, bool FUSED2>
-__global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA,
+//
+// GNA: GroupNorm (+SiLU) of the INPUT operand inside the convolution (north_star (1): "GroupNorm+SiLU ... fused into the
+// prologue"; attention.py:38-39,61, unet_backbone.py:37-38,43-44,215).  Four more warps (10..13) sit between the TMA producer
+// and the MMA issuer: a stage's activation patch lands on the CTA's own afull[s]; the transform warps rewrite it in place
+// as act(a[n][c] * x + b[n][c]) -- ONCE per K-chunk, because all nine taps of the shift-GEMM read the same staged patch --
+// leave halo / out-of-tensor rows at zero (SiLU(b) != 0: the reference zero-pads the ACTIVATED tensor), make the writes
+// visible to the tensor core's async proxy and arrive on the leader's xfull[s]; the issuer waits for xfull[s] (both CTAs'
+// patches transformed) and full[s] (weights).  Per item the warps stage the coefficient rows of the <= gn_nimg images the
+// patch touches and a row map (table offset, or "skip") in shared memory.  Stages of the fused 1x1 second operand (the
+// block input of conv2 + skip) pass through untransformed.
+template <int MT, int TAPS, bool FUSED2, bool GNA>
+__global__ void __launch_bounds__(GNA ? TC2_THREADS + 128 : TC2_THREADS, 1) conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                     const __grid_constant__ CUtensorMap tmB,
                                                                     const __grid_constant__ CUtensorMap tmA2,
                                                                     const __grid_constant__ CUtensorMap tmB2, Tc2Params p) {
@@ -581,8 +620,11 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_c
     uint64_t* bars = (uint64_t*)(bres + (p.b_res ? (size_t)(p.Cin / KC) * p.b_chunk_bytes + (FUSED2 ? (size_t)p.KCH2 * p.b2_chunk_bytes : 0) : 0));
     uint64_t* full = bars;            uint64_t* empty = full + p.S;
     uint64_t* tfull = empty + p.S;    uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+    uint64_t* afull = tempty + 2;     uint64_t* xfull = afull + (GNA ? p.S : 0);        // GNA only
+    uint32_t* tmem_slot = (uint32_t*)(xfull + (GNA ? p.S : 0));
     float* sbias = (float*)(tmem_slot + 4);              // [Cout] bias staged once per CTA (16-byte aligned: the barrier block is)
+    float* gtab = sbias + ((p.Cout + 3) & ~3);           // GNA: [gn_nimg][2][Cin] coefficients of the current item's images
+    uint32_t* rowmeta = (uint32_t*)(gtab + (GNA ? (size_t)p.gn_nimg * 2 * p.Cin : 0));   // GNA: [P] table byte offset of a patch row, ~0u: leave as is
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -605,6 +647,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_c
         }
         for (int i = 0; i < p.S; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 16); }
+        if (GNA) for (int i = 0; i < p.S; ++i) { mbar_init(&afull[i], 1); mbar_init(&xfull[i], 8); }   // 4 transform warps x 2 CTAs
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc2(tmem_slot, 512u);
@@ -616,7 +659,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_c
     pdl_enter();                                         // everything above overlapped the previous kernel's tail
     // The bias vector is read by every epilogue trip; as __ldg float4 loads after the accumulator wait it cost ~25 % of the
     // epilogue at 96 channels (measured when the time bias absorbed conv1's bias).  Stage it in shared memory once.
-    if (p.bias && warp >= 2) {
+    if (p.bias && warp >= 2 && warp < 10) {
         for (int i = threadIdx.x - 64; i < p.Cout; i += TC2_THREADS - 64) sbias[i] = i < p.bias_n ? __ldg(p.bias + i) : 0.f;
         asm volatile("bar.sync 1, %0;" ::"n"(TC2_THREADS - 64) : "memory");      // epilogue warps only
     }
@@ -638,8 +681,10 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_c
                     const bool skipA = (p.exp & 1) && g >= (uint32_t)p.S, skipB = (p.exp & 2) && g >= (uint32_t)p.S;   // diagnostics
                     const bool loadB = !skipB && !(p.b_res && it != pair);       // resident weights arrive with the first item only
                     const int bbytes = second ? p.b2_chunk_bytes : p.b_chunk_bytes;
-                    const uint32_t tx = (uint32_t)(2 * nk * ((skipA ? 0 : p.P * 32) + (loadB ? bbytes : 0)));
+                    // GNA: the patch lands on this CTA's own afull[s] (the transform warps wait there); full[s] counts weights only
+                    const uint32_t tx = (uint32_t)(2 * nk * ((skipA || GNA ? 0 : p.P * 32) + (loadB ? bbytes : 0)));
                     if (leader) { if (tx) mbar_expect_tx(&full[s], tx); else mbar_arrive(&full[s]); }
+                    if (GNA) mbar_expect_tx(&afull[s], (uint32_t)(nk * p.P * 32));
                     uint8_t* sbase = ring + (size_t)s * p.stage_bytes;
                     const CUtensorMap* mA = second ? &tmA2 : &tmA;
                     const CUtensorMap* mB = second ? &tmB2 : &tmB;
@@ -649,8 +694,12 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_c
                                       : (second ? bres + (size_t)KCH * p.b_chunk_bytes + (size_t)kc0 * p.b2_chunk_bytes
                                                 : bres + (size_t)(kc0 + k) * p.b_chunk_bytes);
                         const int row0 = Q0 - halo_rows;
-                        for (int r = 0; r < p.P && !skipA; r += p.seg)
-                            tma2_load_2d(adst + (size_t)r * 32, mA, fbar, (kc0 + k) * KC, row0 + r);
+                        if (GNA) {
+                            for (int r = 0; r < p.P; r += p.seg) tma_load_2d(adst + (size_t)r * 32, mA, &afull[s], (kc0 + k) * KC, row0 + r);
+                        } else {
+                            for (int r = 0; r < p.P && !skipA; r += p.seg)
+                                tma2_load_2d(adst + (size_t)r * 32, mA, fbar, (kc0 + k) * KC, row0 + r);
+                        }
                         if (loadB) tma2_load_3d(bdst, mB, fbar, (kc0 + k) * KC, nrow0, 0);
                     }
                 }
@@ -683,6 +732,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_c
                 for (int st = 0; st < NST; ++st, ++g) {
                     const uint32_t s = g % (uint32_t)p.S; const uint32_t ph = (g / (uint32_t)p.S) & 1;
                     mbar_wait(&full[s], ph);
+                    if (GNA) mbar_wait_acq_cluster(&xfull[s], ph);      // both CTAs' patches transformed
                     tc_fence_after();
                     uint32_t a_lo = ring_lo + s * stage16;
                     if (FUSED2 && st >= NST - KCH2) {
@@ -718,6 +768,91 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const __grid_c
                 }
                 if (el) umma2_commit_mc(&tfull[buf]);
                 __syncwarp();
+            }
+        }
+    } else if (GNA && warp >= 10) {
+        // ===================================================================== operand transform (both CTAs)
+        // Thread tt owns the 16-byte packets pk = tt + 128 j of a patch (row pk >> 1): conflict-free LDS/STS.128, and
+        // because rows advance by 64 per j the SWIZZLE_32B chunk bit (row >> 2) & 1 -- hence the eight channels a thread
+        // works on -- is the same for all of its packets, so its coefficients stay in registers across a stage.
+        const int tt = threadIdx.x - TC2_THREADS;
+        const int HpWp = p.Hp * p.Wp;
+        const int lc8 = ((tt & 1) ^ ((tt >> 3) & 1)) << 3;
+        const float hs = p.gn_act ? 0.5f : 1.0f;          // SiLU through tanh: the affine produces z / 2 (common.cuh silu_half)
+        const uint32_t xbar0 = mapa_u32(smem_u32(&xfull[0]), 0);
+        const int C2 = 2 * p.Cin;
+        const uint32_t gtab_u = smem_u32(gtab), ring_u = smem_u32(ring);
+        const uint32_t chunk_stride = (uint32_t)(p.a_chunk_bytes + (p.b_res ? 0 : p.b_chunk_bytes));
+        uint32_t g = 0;
+        for (int it = pair; it < p.items; it += npairs) {
+            const int pt = it / p.n_tiles;
+            const int row0 = pt * (2 * tile_rows) + (int)rank * tile_rows - halo_rows;
+            asm volatile("bar.sync 2, 128;" ::: "memory");       // the previous item's table / row map are no longer read
+            const int qa = max(row0, 0), qb = min(row0 + p.P, p.Qtot) - 1;
+            const int n_first = qa / HpWp;
+            if (qb >= qa) {
+                const int nimg = qb / HpWp - n_first + 1;
+                const float4* src = reinterpret_cast<const float4*>(p.gn_ab + (size_t)n_first * C2);
+                float4* dst = reinterpret_cast<float4*>(gtab);
+                for (int i = tt; i < nimg * (C2 >> 2); i += 128) {
+                    float4 v = __ldg(src + i);
+                    v.x *= hs; v.y *= hs; v.z *= hs; v.w *= hs;
+                    dst[i] = v;
+                }
+            }
+            for (int r = tt; r < p.P; r += 128) {
+                const int Q = row0 + r;
+                uint32_t m = 0xFFFFFFFFu;
+                if (Q >= 0 && Q < p.Qtot) {
+                    const int n = Q / HpWp, rem = Q - n * HpWp, yp = rem / p.Wp, xp = rem - yp * p.Wp;
+                    if (yp >= 1 && yp <= p.H && xp >= 1 && xp <= p.W) m = (uint32_t)((n - n_first) * C2 * 4);
+                }
+                rowmeta[r] = m;
+            }
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+            for (int st = 0; st < NST; ++st, ++g) {
+                const uint32_t s = g % (uint32_t)p.S; const uint32_t ph = (g / (uint32_t)p.S) & 1;
+                mbar_wait(&afull[s], ph);
+                if (!(FUSED2 && st >= NST - KCH2)) {
+                    const int kc0 = st * p.KS, nk = min(p.KS, KCH - kc0);
+                    for (int k = 0; k < nk; ++k) {
+                        const uint32_t abase = ring_u + s * (uint32_t)p.stage_bytes + (uint32_t)k * chunk_stride;
+                        const uint32_t coff = (uint32_t)(((kc0 + k) * KC + lc8) * 4);
+                        uint32_t cur = 0xFFFFFFFFu;
+                        float ca[8], cb[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { ca[i] = 0.f; cb[i] = 0.f; }
+#pragma unroll 2
+                        for (int pk = tt; pk < 2 * p.P; pk += 128) {
+                            const uint32_t m = rowmeta[pk >> 1];
+                            if (m == 0xFFFFFFFFu) continue;
+                            if (m != cur) {
+                                cur = m;
+                                const uint32_t ta = gtab_u + m + coff, tb = ta + (uint32_t)p.Cin * 4u;
+                                const uint4 a0 = lds128u(ta), a1 = lds128u(ta + 16), b0 = lds128u(tb), b1 = lds128u(tb + 16);
+                                ca[0] = __uint_as_float(a0.x); ca[1] = __uint_as_float(a0.y); ca[2] = __uint_as_float(a0.z); ca[3] = __uint_as_float(a0.w);
+                                ca[4] = __uint_as_float(a1.x); ca[5] = __uint_as_float(a1.y); ca[6] = __uint_as_float(a1.z); ca[7] = __uint_as_float(a1.w);
+                                cb[0] = __uint_as_float(b0.x); cb[1] = __uint_as_float(b0.y); cb[2] = __uint_as_float(b0.z); cb[3] = __uint_as_float(b0.w);
+                                cb[4] = __uint_as_float(b1.x); cb[5] = __uint_as_float(b1.y); cb[6] = __uint_as_float(b1.z); cb[7] = __uint_as_float(b1.w);
+                            }
+                            const uint32_t addr = abase + (uint32_t)pk * 16u;
+                            const uint4 q = lds128u(addr);
+                            uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                float lo = fmaf(__uint_as_float(w[i] << 16), ca[2 * i], cb[2 * i]);
+                                float hi = fmaf(__uint_as_float(w[i] & 0xffff0000u), ca[2 * i + 1], cb[2 * i + 1]);
+                                if (p.gn_act) { lo = silu_half(lo); hi = silu_half(hi); }
+                                const __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
+                                w[i] = *reinterpret_cast<const uint32_t*>(&h2);
+                            }
+                            sts128u(addr, make_uint4(w[0], w[1], w[2], w[3]));
+                        }
+                    }
+                }
+                fence_proxy_async();                      // generic-proxy writes -> visible to the tensor core (async proxy)
+                __syncwarp();
+                if (lane == 0) mbar_arrive_release_cluster(xbar0 + s * 8u);
             }
         }
     } else {
@@ -905,7 +1040,13 @@ static int conv_tc2_launch(const ddpm_conv_args* a, cudaStream_t st) {
     p.KS = p.taps > 1 ? 1 : (KCH < 4 ? KCH : 4);
     p.KCH2 = a->in2.ptr ? a->in2.C / KC : 0;                // fused 1x1 second operand (3x3 main conv only: KS == 1)
     p.b2_chunk_bytes = (p.NT / 2) * 32;
-    const int budget = 212 * 1024;
+    p.gn_ab = a->gn_ab; p.gn_act = a->gn_act; p.gn_nimg = 0;
+    size_t gn_bytes = 0;
+    if (p.gn_ab) {
+        p.gn_nimg = (p.P + p.Hp * p.Wp - 2) / (p.Hp * p.Wp) + 1;
+        gn_bytes = (size_t)p.gn_nimg * 2 * p.Cin * 4 + (size_t)p.P * 4 + 8 * 2 * 12;       // table + row map + afull / xfull
+    }
+    const int budget = 212 * 1024 - (int)((gn_bytes + 1023) & ~(size_t)1023);
     p.pix_tiles = ceil_div(p.Qtot, 256 * MT);
     p.items = p.pix_tiles * p.n_tiles;
     int pairs = sm_count() / 2; if (pairs > p.items) pairs = p.items; if (pairs < 1) pairs = 1;
@@ -926,7 +1067,7 @@ static int conv_tc2_launch(const ddpm_conv_args* a, cudaStream_t st) {
     }
     if (p.S < 2) return DDPM_E_ARG;
     size_t smem = (size_t)p.S * p.stage_bytes + (p.b_res ? (size_t)KCH * p.b_chunk_bytes + (size_t)p.KCH2 * p.b2_chunk_bytes : 0) +
-                  8 * (2 * p.S + 4) + 16 + (size_t)p.Cout * 4 + 1024;
+                  8 * (2 * p.S + 4) + 16 + (size_t)p.Cout * 4 + 1024 + gn_bytes + 16;
 
     CUtensorMap tmA, tmB, tmA2, tmB2;
     if (p.KCH2) {
@@ -950,20 +1091,25 @@ static int conv_tc2_launch(const ddpm_conv_args* a, cudaStream_t st) {
         if (encode(&tmB, (void*)a->w, 3, db, sb, bb, CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(TC2_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(p.gn_ab ? TC2_THREADS + 128 : TC2_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute at[2]; unsigned nat = 1;
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     pdl_attr(at, &nat);
     cfg.attrs = at; cfg.numAttrs = nat;
-    static size_t configured[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#define TC2_GO(MTV, TAPSV, F2, SLOT) { \
-        if (smem > configured[SLOT]) { CUDA_TRY(cudaFuncSetAttribute(conv_tc2_kernel<MTV, TAPSV, F2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured[SLOT] = smem; } \
-        CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<MTV, TAPSV, F2>, tmA, tmB, F2 ? tmA2 : tmA, F2 ? tmB2 : tmB, p)); }
-    if (p.KCH2) { if (MT == 2) TC2_GO(2, 9, true, 4) else TC2_GO(1, 9, true, 5) }
-    else if (p.taps == 4) { if (MT == 2) TC2_GO(2, 4, false, 6) else TC2_GO(1, 4, false, 7) }
-    else if (MT == 2) { if (p.taps == 9) TC2_GO(2, 9, false, 0) else TC2_GO(2, 1, false, 1) }
-    else { if (p.taps == 9) TC2_GO(1, 9, false, 2) else TC2_GO(1, 1, false, 3) }
+    static size_t configured[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#define TC2_GO(MTV, TAPSV, F2, GN, SLOT) { \
+        if (smem > configured[SLOT]) { CUDA_TRY(cudaFuncSetAttribute(conv_tc2_kernel<MTV, TAPSV, F2, GN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured[SLOT] = smem; } \
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<MTV, TAPSV, F2, GN>, tmA, tmB, F2 ? tmA2 : tmA, F2 ? tmB2 : tmB, p)); }
+    if (p.gn_ab) {
+        if (p.KCH2) { if (MT == 2) TC2_GO(2, 9, true, true, 8) else TC2_GO(1, 9, true, true, 9) }
+        else if (MT == 2) { if (p.taps == 9) TC2_GO(2, 9, false, true, 10) else TC2_GO(2, 1, false, true, 11) }
+        else { if (p.taps == 9) TC2_GO(1, 9, false, true, 12) else TC2_GO(1, 1, false, true, 13) }
+    }
+    else if (p.KCH2) { if (MT == 2) TC2_GO(2, 9, true, false, 4) else TC2_GO(1, 9, true, false, 5) }
+    else if (p.taps == 4) { if (MT == 2) TC2_GO(2, 4, false, false, 6) else TC2_GO(1, 4, false, false, 7) }
+    else if (MT == 2) { if (p.taps == 9) TC2_GO(2, 9, false, false, 0) else TC2_GO(2, 1, false, false, 1) }
+    else { if (p.taps == 9) TC2_GO(1, 9, false, false, 2) else TC2_GO(1, 1, false, false, 3) }
 #undef TC2_GO
     LAUNCH_OK();
     return 0;

@@ -193,6 +193,7 @@ struct GnP {
     const uint64_t* rng; uint32_t layer;
     const float* gamma; const float* beta;
     double* stats;               // [N][G][2] (sum, sum of squares)
+    float* ab;                   // MODE 3: [N][2][C] affine of the normalisation, z = ab[n][0][c] * x + ab[n][1][c]
     float* dgamma; float* dbeta; // backward: accumulated with atomics (may be NULL)
     float* cs_nc; float* cs_c;   // backward: per-image / total channel sums of the final dx (conv bias and time-bias gradients)
     int accumulate;              // backward: dx += ...
@@ -242,7 +243,8 @@ __device__ __forceinline__ void cta_channel_reduce(float (*part)[NT], const floa
     __syncthreads();
 }
 
-// MODE 0: fused stats + apply; 1: stats only; 2: apply only (stats given)
+// MODE 0: fused stats + apply; 1: stats only; 2: apply only (stats given); 3: stats -> per-(image, channel) affine
+// coefficients for the convolution that applies GroupNorm (+SiLU) to its own input operand (conv_tc.cu, gn_ab)
 template <typename T, int VEC, int MODE>
 __global__ void __launch_bounds__(NT, GN_FWD_OCC) gn_fwd_kernel(GnP a) {
     extern __shared__ __align__(16) unsigned char gsm[];
@@ -296,13 +298,22 @@ __global__ void __launch_bounds__(NT, GN_FWD_OCC) gn_fwd_kernel(GnP a) {
                 const double* rp = cl.map_shared_rank(gpart, r);
                 s += rp[g]; q += rp[G + g];
             }
-            if (rank == 0) { a.stats[((size_t)n * G + g) * 2] = s; a.stats[((size_t)n * G + g) * 2 + 1] = q; }
+            if (rank == 0 && a.stats) { a.stats[((size_t)n * G + g) * 2] = s; a.stats[((size_t)n * G + g) * 2 + 1] = q; }
             const double cnt = (double)cpg * HW, mu = s / cnt;
             double var = q / cnt - mu * mu; if (var < 0.0) var = 0.0;
             gm[g] = (float)mu; gr[g] = (float)(1.0 / sqrt(var + (double)a.eps));
         }
         cluster_arrive();                                    // remote reads done; waited for before exit
         __syncthreads();
+        if (MODE == 3 && rank == 0) {
+            float* ab = a.ab + (size_t)n * 2 * C;
+            for (int c = threadIdx.x; c < C; c += NT) {
+                const int g = c / cpg;
+                const float sc = gr[g] * __ldg(a.gamma + c);
+                ab[c] = sc;
+                ab[C + c] = __ldg(a.beta + c) - gm[g] * sc;
+            }
+        }
     } else {
         for (int g = threadIdx.x; g < G; g += NT) {
             const double s = a.stats[((size_t)n * G + g) * 2], q = a.stats[((size_t)n * G + g) * 2 + 1];
@@ -313,7 +324,7 @@ __global__ void __launch_bounds__(NT, GN_FWD_OCC) gn_fwd_kernel(GnP a) {
         __syncthreads();
     }
 
-    if (MODE != 1 && m.active) {
+    if ((MODE == 0 || MODE == 2) && m.active) {
         float sc[VEC], sh[VEC];
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
@@ -1025,7 +1036,7 @@ static int gn_fill(GnP& p, const ddpm_tensor* x, int groups, const double* stats
     p.thr16 = p_drop > 0.f ? (uint32_t)(p_drop * 65536.0f + 0.5f) : 0u;
     p.keep_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
     p.rng = rng; p.layer = layer; p.gamma = gamma; p.beta = beta; p.stats = const_cast<double*>(stats);
-    p.dgamma = p.dbeta = nullptr; p.cs_nc = p.cs_c = nullptr; p.accumulate = 0; p.stash = 0; p.wshift = log2_exact(x->W);
+    p.ab = nullptr; p.dgamma = p.dbeta = nullptr; p.cs_nc = p.cs_c = nullptr; p.accumulate = 0; p.stash = 0; p.wshift = log2_exact(x->W);
     return 0;
 }
 
@@ -1037,8 +1048,8 @@ static int gn_fwd_dispatch(GnP& p, const ddpm_tensor* x, const ddpm_tensor* out,
         int cs = MODE == 2 ? 1 : gn_cluster_size(HW, cvs, x->N); \
         if (MODE == 2) { cs = 1; int want = (HW * cvs) / (NT * 16); while (cs < 8 && cs < want) cs <<= 1; } \
         return launch_cluster(gn_fwd_kernel<T, VEC, MODE>, x->N * cs, cs, sm0 + gn_ring_bytes<VEC, 1, GN_PIPE_D_FWD>(), st, p); }
-    const bool v8 = vec_ok(x, 8, 2) && (MODE == 1 || vec_ok(out, 8, 2));
-    const bool v4 = vec_ok(x, 4, 4) && (MODE == 1 || vec_ok(out, 4, 4));
+    const bool v8 = vec_ok(x, 8, 2) && (MODE == 1 || MODE == 3 || vec_ok(out, 8, 2));
+    const bool v4 = vec_ok(x, 4, 4) && (MODE == 1 || MODE == 3 || vec_ok(out, 4, 4));
     if (MODE == 0 && dtype == DDPM_BF16 && v8 && gn_slab_tensor_ok(x) && gn_slab_tensor_ok(out)) {
         size_t smem = 0; int occ = 0; SlabP sp;
         const int cs = gn_slab_plan(x, 1, sm0, &sp, &smem, &occ);
@@ -1064,6 +1075,14 @@ extern "C" int ddpm_gn_stats(const ddpm_tensor* x, int dtype, int groups, double
     GnP p; int rc = gn_fill(p, x, groups, stats, nullptr, nullptr, 0.f, 0, 0.f, nullptr, 0); if (rc) return rc;
     p.o = p.x; p.dy = p.x;
     return gn_fwd_dispatch<1>(p, x, x, dtype, (cudaStream_t)stream);
+}
+
+extern "C" int ddpm_gn_coeffs(const ddpm_tensor* x, int dtype, int groups, const float* gamma, const float* beta, float eps,
+                              float* ab, void* stream) {
+    if (!tensor_ok(x) || !ab || !gamma || !beta || groups <= 0 || x->C % groups) return DDPM_E_ARG;
+    GnP p; int rc = gn_fill(p, x, groups, nullptr, gamma, beta, eps, 0, 0.f, nullptr, 0); if (rc) return rc;
+    p.o = p.x; p.dy = p.x; p.ab = ab;
+    return gn_fwd_dispatch<3>(p, x, x, dtype, (cudaStream_t)stream);
 }
 
 extern "C" int ddpm_gn_apply(const ddpm_tensor* x, int dtype, int groups, const double* stats, const float* gamma,
