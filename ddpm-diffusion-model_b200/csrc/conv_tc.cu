@@ -507,23 +507,20 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     // to drain (ncu: MEMBAR + ERRBAR = 16 % of the stall samples) for no reason
     asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t cluster_addr) {
-    // publishes this warp's shared-memory writes (already made visible to the async proxy by fence.proxy.async) to the
-    // MMA-issuing thread of the pair's leader CTA
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+__device__ __forceinline__ void mbar_arrive_xform(uint32_t cluster_addr) {
+    // "this warp's rewrite of its patch rows is done".  The rows live in the arriving CTA's OWN shared memory and are read by
+    // that SM's tensor core; each writer has already executed fence.proxy.async, so the data is in place before the signal
+    // leaves.  A release at cluster scope here compiled to MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR per arrive (and the matching
+    // acquire.cluster wait to CCTL.IVALL in the MMA-issue loop): ncu had the kernel at 3x the unfused time with those.
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-__device__ __forceinline__ void mbar_wait_acq_cluster(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAITC_%=:\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONEC_%=;\n\t"
-        "bra WAITC_%=;\n\t"
-        "DONEC_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+__device__ __forceinline__ uint32_t lds32u(uint32_t a) {
+    uint32_t v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a)); return v;
 }
+__device__ __forceinline__ void sts32u(uint32_t a, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ uint4 lds128u(uint32_t a) {
     uint4 v;
-    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
     return v;
 }
 __device__ __forceinline__ void sts128u(uint32_t a, const uint4& v) {
@@ -567,6 +564,63 @@ __device__ __forceinline__ void ldg256(const void* p, U8& v) {
 __device__ __forceinline__ void stg256(void* p, const uint4& lo, const uint4& hi) {
     asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                  ::"l"(p), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
+}
+
+// ---- GroupNorm (+SiLU) operand transform of one staged K-chunk (conv_tc2_kernel GNA, warps 10..13) ------------------------
+// A transform warp runs alone on its scheduler, so throughput is ILP: the first version (one packet at a time, a
+// "coefficients changed?" branch per packet) issued one instruction per ~8 cycles and made the convolution 2.3x slower
+// (ncu: stall_wait everywhere, tensor pipe 25 %).  Here NB packets are in flight per thread and the body is branch-free
+// (skip rows are computed and not stored), so the 8 x NB element chains interleave; the floor is the MUFU: 8 tanh per
+// packet = 64 issue cycles per warp.
+__device__ __forceinline__ void gn_ld8(uint32_t a, float* v) {
+    const uint4 x = lds128u(a), y = lds128u(a + 16);
+    v[0] = __uint_as_float(x.x); v[1] = __uint_as_float(x.y); v[2] = __uint_as_float(x.z); v[3] = __uint_as_float(x.w);
+    v[4] = __uint_as_float(y.x); v[5] = __uint_as_float(y.y); v[6] = __uint_as_float(y.z); v[7] = __uint_as_float(y.w);
+}
+template <bool ACT>
+__device__ __forceinline__ uint4 gn_xform_packet(const uint4& q, const float* ca, const float* cb) {
+    uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float lo = fmaf(__uint_as_float(w[i] << 16), ca[2 * i], cb[2 * i]);
+        float hi = fmaf(__uint_as_float(w[i] & 0xffff0000u), ca[2 * i + 1], cb[2 * i + 1]);
+        if (ACT) { lo = silu_half(lo); hi = silu_half(hi); }
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
+        w[i] = *reinterpret_cast<const uint32_t*>(&h2);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+// abase: the chunk in shared memory; mt_u: row map; tabc: coefficient table + this thread's channel offset; cin4 = Cin * 4
+template <bool ACT, bool SINGLE>
+__device__ __forceinline__ void gn_xform_chunk(uint32_t abase, uint32_t mt_u, uint32_t tabc, uint32_t cin4, int tt, int npk) {
+    constexpr int NB = SINGLE ? 4 : 2;
+    float ca[8], cb[8];
+    if (SINGLE) { gn_ld8(tabc, ca); gn_ld8(tabc + cin4, cb); }
+#pragma unroll 1
+    for (int pk0 = tt; pk0 < npk; pk0 += 128 * NB) {
+        uint32_t m[NB]; uint4 q[NB];
+        float la[SINGLE ? 1 : NB][8], lb[SINGLE ? 1 : NB][8];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const int pk = pk0 + 128 * b;
+            const int pkc = pk < npk ? pk : tt;                  // out of range: load something valid, store nothing
+            m[b] = lds32u(mt_u + (uint32_t)(pkc >> 1) * 4u);
+            if (pk >= npk) m[b] = 0xFFFFFFFFu;
+            q[b] = lds128u(abase + (uint32_t)pkc * 16u);
+        }
+        if (!SINGLE) {
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                const uint32_t t = tabc + (m[b] == 0xFFFFFFFFu ? 0u : m[b]);
+                gn_ld8(t, la[b]); gn_ld8(t + cin4, lb[b]);
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const uint4 o = SINGLE ? gn_xform_packet<ACT>(q[b], ca, cb) : gn_xform_packet<ACT>(q[b], la[b], lb[b]);
+            if (m[b] != 0xFFFFFFFFu) sts128u(abase + (uint32_t)(pk0 + 128 * b) * 16u, o);
+        }
+    }
 }
 
 struct Tc2Params {
@@ -623,8 +677,8 @@ __global__ void __launch_bounds__(GNA ? TC2_THREADS + 128 : TC2_THREADS, 1) conv
     uint64_t* afull = tempty + 2;     uint64_t* xfull = afull + (GNA ? p.S : 0);        // GNA only
     uint32_t* tmem_slot = (uint32_t*)(xfull + (GNA ? p.S : 0));
     float* sbias = (float*)(tmem_slot + 4);              // [Cout] bias staged once per CTA (16-byte aligned: the barrier block is)
-    float* gtab = sbias + ((p.Cout + 3) & ~3);           // GNA: [gn_nimg][2][Cin] coefficients of the current item's images
-    uint32_t* rowmeta = (uint32_t*)(gtab + (GNA ? (size_t)p.gn_nimg * 2 * p.Cin : 0));   // GNA: [P] table byte offset of a patch row, ~0u: leave as is
+    float* gtab = sbias + ((p.Cout + 3) & ~3);           // GNA: [2 buffers][gn_nimg][2][Cin] coefficients of an item's images
+    // GNA: behind the two table buffers, [2][P] row maps (table byte offset of a patch row, ~0u: leave the row as it is)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -732,7 +786,7 @@ __global__ void __launch_bounds__(GNA ? TC2_THREADS + 128 : TC2_THREADS, 1) conv
                 for (int st = 0; st < NST; ++st, ++g) {
                     const uint32_t s = g % (uint32_t)p.S; const uint32_t ph = (g / (uint32_t)p.S) & 1;
                     mbar_wait(&full[s], ph);
-                    if (GNA) mbar_wait_acq_cluster(&xfull[s], ph);      // both CTAs' patches transformed
+                    if (GNA) mbar_wait(&xfull[s], ph);                  // both CTAs' patches transformed
                     tc_fence_after();
                     uint32_t a_lo = ring_lo + s * stage16;
                     if (FUSED2 && st >= NST - KCH2) {
@@ -775,31 +829,34 @@ __global__ void __launch_bounds__(GNA ? TC2_THREADS + 128 : TC2_THREADS, 1) conv
         // Thread tt owns the 16-byte packets pk = tt + 128 j of a patch (row pk >> 1): conflict-free LDS/STS.128, and
         // because rows advance by 64 per j the SWIZZLE_32B chunk bit (row >> 2) & 1 -- hence the eight channels a thread
         // works on -- is the same for all of its packets, so its coefficients stay in registers across a stage.
+        // The coefficient table and the row map are double buffered: item i+1's are prepared (cp.async for the table) while
+        // item i is being transformed, so one named barrier per item is the only per-item serialisation.
         const int tt = threadIdx.x - TC2_THREADS;
         const int HpWp = p.Hp * p.Wp;
         const int lc8 = ((tt & 1) ^ ((tt >> 3) & 1)) << 3;
-        const float hs = p.gn_act ? 0.5f : 1.0f;          // SiLU through tanh: the affine produces z / 2 (common.cuh silu_half)
         const uint32_t xbar0 = mapa_u32(smem_u32(&xfull[0]), 0);
         const int C2 = 2 * p.Cin;
-        const uint32_t gtab_u = smem_u32(gtab), ring_u = smem_u32(ring);
+        // explicit ld/st.shared below: through generic pointers the compiler emitted LD.E / ST.E (address space lost)
+        const uint32_t ring_u = smem_u32(ring);
+        const uint32_t tab_bytes = (uint32_t)(p.gn_nimg * C2 * 4), meta_bytes = (uint32_t)(p.P * 4);
+        const uint32_t gtab_u = smem_u32(gtab), meta_u = gtab_u + 2u * tab_bytes;
         const uint32_t chunk_stride = (uint32_t)(p.a_chunk_bytes + (p.b_res ? 0 : p.b_chunk_bytes));
-        uint32_t g = 0;
-        for (int it = pair; it < p.items; it += npairs) {
+        const uint32_t flag_u = meta_u + 2u * meta_bytes;      // [2] "the item's patch lies inside one image"
+        auto prepare = [&](int it, uint32_t buf) {          // coefficient rows + row map of item `it` into buffer `buf`
             const int pt = it / p.n_tiles;
             const int row0 = pt * (2 * tile_rows) + (int)rank * tile_rows - halo_rows;
-            asm volatile("bar.sync 2, 128;" ::: "memory");       // the previous item's table / row map are no longer read
             const int qa = max(row0, 0), qb = min(row0 + p.P, p.Qtot) - 1;
             const int n_first = qa / HpWp;
+            int nimg = 0;
             if (qb >= qa) {
-                const int nimg = qb / HpWp - n_first + 1;
-                const float4* src = reinterpret_cast<const float4*>(p.gn_ab + (size_t)n_first * C2);
-                float4* dst = reinterpret_cast<float4*>(gtab);
-                for (int i = tt; i < nimg * (C2 >> 2); i += 128) {
-                    float4 v = __ldg(src + i);
-                    v.x *= hs; v.y *= hs; v.z *= hs; v.w *= hs;
-                    dst[i] = v;
-                }
+                nimg = qb / HpWp - n_first + 1;
+                const float* src = p.gn_ab + (size_t)n_first * C2;
+                const uint32_t dst = gtab_u + buf * tab_bytes;
+                for (int i = tt; i < nimg * (C2 >> 2); i += 128)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)i * 16u), "l"(src + 4 * i) : "memory");
             }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            if (tt == 0) sts32u(flag_u + buf * 4u, nimg <= 1 ? 1u : 0u);
             for (int r = tt; r < p.P; r += 128) {
                 const int Q = row0 + r;
                 uint32_t m = 0xFFFFFFFFu;
@@ -807,9 +864,30 @@ __global__ void __launch_bounds__(GNA ? TC2_THREADS + 128 : TC2_THREADS, 1) conv
                     const int n = Q / HpWp, rem = Q - n * HpWp, yp = rem / p.Wp, xp = rem - yp * p.Wp;
                     if (yp >= 1 && yp <= p.H && xp >= 1 && xp <= p.W) m = (uint32_t)((n - n_first) * C2 * 4);
                 }
-                rowmeta[r] = m;
+                sts32u(meta_u + buf * meta_bytes + (uint32_t)r * 4u, m);
             }
-            asm volatile("bar.sync 2, 128;" ::: "memory");
+            return nimg;
+        };
+        uint32_t g = 0, j = 0;
+        int nimg_cur = 0, nimg_next = 0;
+        if (pair < p.items) nimg_next = prepare(pair, 0u);
+        for (int it = pair; it < p.items; it += npairs, ++j) {
+            const uint32_t buf = j & 1;
+            nimg_cur = nimg_next;
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            if (p.gn_act) {                                      // SiLU through tanh: the affine produces z / 2 -- halve the rows this thread copied
+                const uint32_t dst = gtab_u + buf * tab_bytes;
+                for (int i = tt; i < nimg_cur * (C2 >> 2); i += 128) {
+                    uint4 v = lds128u(dst + (uint32_t)i * 16u);
+                    v.x = __float_as_uint(0.5f * __uint_as_float(v.x)); v.y = __float_as_uint(0.5f * __uint_as_float(v.y));
+                    v.z = __float_as_uint(0.5f * __uint_as_float(v.z)); v.w = __float_as_uint(0.5f * __uint_as_float(v.w));
+                    sts128u(dst + (uint32_t)i * 16u, v);
+                }
+            }
+            asm volatile("bar.sync 2, 128;" ::: "memory");       // item `it`'s table / row map complete; the other buffer is free
+            if (it + npairs < p.items) nimg_next = prepare(it + npairs, buf ^ 1u);
+            const uint32_t tab_u = gtab_u + buf * tab_bytes, mt_u = meta_u + buf * meta_bytes;
+            const bool single = lds32u(flag_u + buf * 4u) != 0u;
             for (int st = 0; st < NST; ++st, ++g) {
                 const uint32_t s = g % (uint32_t)p.S; const uint32_t ph = (g / (uint32_t)p.S) & 1;
                 mbar_wait(&afull[s], ph);
@@ -817,44 +895,18 @@ __global__ void __launch_bounds__(GNA ? TC2_THREADS + 128 : TC2_THREADS, 1) conv
                     const int kc0 = st * p.KS, nk = min(p.KS, KCH - kc0);
                     for (int k = 0; k < nk; ++k) {
                         const uint32_t abase = ring_u + s * (uint32_t)p.stage_bytes + (uint32_t)k * chunk_stride;
-                        const uint32_t coff = (uint32_t)(((kc0 + k) * KC + lc8) * 4);
-                        uint32_t cur = 0xFFFFFFFFu;
-                        float ca[8], cb[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) { ca[i] = 0.f; cb[i] = 0.f; }
-#pragma unroll 2
-                        for (int pk = tt; pk < 2 * p.P; pk += 128) {
-                            const uint32_t m = rowmeta[pk >> 1];
-                            if (m == 0xFFFFFFFFu) continue;
-                            if (m != cur) {
-                                cur = m;
-                                const uint32_t ta = gtab_u + m + coff, tb = ta + (uint32_t)p.Cin * 4u;
-                                const uint4 a0 = lds128u(ta), a1 = lds128u(ta + 16), b0 = lds128u(tb), b1 = lds128u(tb + 16);
-                                ca[0] = __uint_as_float(a0.x); ca[1] = __uint_as_float(a0.y); ca[2] = __uint_as_float(a0.z); ca[3] = __uint_as_float(a0.w);
-                                ca[4] = __uint_as_float(a1.x); ca[5] = __uint_as_float(a1.y); ca[6] = __uint_as_float(a1.z); ca[7] = __uint_as_float(a1.w);
-                                cb[0] = __uint_as_float(b0.x); cb[1] = __uint_as_float(b0.y); cb[2] = __uint_as_float(b0.z); cb[3] = __uint_as_float(b0.w);
-                                cb[4] = __uint_as_float(b1.x); cb[5] = __uint_as_float(b1.y); cb[6] = __uint_as_float(b1.z); cb[7] = __uint_as_float(b1.w);
-                            }
-                            const uint32_t addr = abase + (uint32_t)pk * 16u;
-                            const uint4 q = lds128u(addr);
-                            uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                float lo = fmaf(__uint_as_float(w[i] << 16), ca[2 * i], cb[2 * i]);
-                                float hi = fmaf(__uint_as_float(w[i] & 0xffff0000u), ca[2 * i + 1], cb[2 * i + 1]);
-                                if (p.gn_act) { lo = silu_half(lo); hi = silu_half(hi); }
-                                const __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
-                                w[i] = *reinterpret_cast<const uint32_t*>(&h2);
-                            }
-                            sts128u(addr, make_uint4(w[0], w[1], w[2], w[3]));
-                        }
+                        const uint32_t tabc = tab_u + (uint32_t)(((kc0 + k) * KC + lc8) * 4);
+                        const uint32_t cin4 = (uint32_t)p.Cin * 4u;
+                        if (p.gn_act) { if (single) gn_xform_chunk<true, true>(abase, mt_u, tabc, cin4, tt, 2 * p.P); else gn_xform_chunk<true, false>(abase, mt_u, tabc, cin4, tt, 2 * p.P); }
+                        else { if (single) gn_xform_chunk<false, true>(abase, mt_u, tabc, cin4, tt, 2 * p.P); else gn_xform_chunk<false, false>(abase, mt_u, tabc, cin4, tt, 2 * p.P); }
                     }
                 }
                 fence_proxy_async();                      // generic-proxy writes -> visible to the tensor core (async proxy)
                 __syncwarp();
-                if (lane == 0) mbar_arrive_release_cluster(xbar0 + s * 8u);
+                if (lane == 0) mbar_arrive_xform(xbar0 + s * 8u);
             }
         }
+        asm volatile("cp.async.wait_all;" ::: "memory");
     } else {
         // ===================================================================== epilogue (both CTAs)
         const int qd = warp & 3;                          // TMEM lane quarter this warp may read (warp id % 4)
@@ -1044,7 +1096,7 @@ static int conv_tc2_launch(const ddpm_conv_args* a, cudaStream_t st) {
     size_t gn_bytes = 0;
     if (p.gn_ab) {
         p.gn_nimg = (p.P + p.Hp * p.Wp - 2) / (p.Hp * p.Wp) + 1;
-        gn_bytes = (size_t)p.gn_nimg * 2 * p.Cin * 4 + (size_t)p.P * 4 + 8 * 2 * 12;       // table + row map + afull / xfull
+        gn_bytes = 2 * ((size_t)p.gn_nimg * 2 * p.Cin * 4 + (size_t)p.P * 4) + 16 + 8 * 2 * 12;   // 2 x (table + row map) + flags + afull / xfull
     }
     const int budget = 212 * 1024 - (int)((gn_bytes + 1023) & ~(size_t)1023);
     p.pix_tiles = ceil_div(p.Qtot, 256 * MT);

@@ -401,8 +401,12 @@ def gn_stats(E: Exec, x: Act, groups: int) -> torch.Tensor:
 
 
 def fuse_gn_enabled() -> bool:
+    """Opt-in (DDPM_B200_FUSE_GN=1).  Measured on B200 (profiles/r2_gn_operand_fusion.txt): the fused form is bit-identical to
+    the two-launch form but slower -- the transform costs ~7.5 instructions per element on warps that run alone on their
+    scheduler, over a patch that is 1.5x the tile (halo) and is re-transformed per output-channel tile: 96->96@64, B=256:
+    47 + 236 us against 103 + 135 us; DDIM-100 350 against 390 samples/s."""
     import os
-    return os.environ.get("DDPM_B200_FUSE_GN", "1") != "0"
+    return os.environ.get("DDPM_B200_FUSE_GN", "0") == "1"
 
 
 def gn_fusable(E: Exec, x: Act, cout: int, k: int, in2: Optional[Act] = None) -> bool:
