@@ -891,7 +891,7 @@ __global__ void __launch_bounds__(GNA ? TC2_THREADS + 128 : TC2_THREADS, 1) conv
             for (int st = 0; st < NST; ++st, ++g) {
                 const uint32_t s = g % (uint32_t)p.S; const uint32_t ph = (g / (uint32_t)p.S) & 1;
                 mbar_wait(&afull[s], ph);
-                if (!(FUSED2 && st >= NST - KCH2)) {
+                if (!(FUSED2 && st >= NST - KCH2) && !(p.exp & 4096)) {      // exp bit 12: skip the transform (timing diagnostic)
                     const int kc0 = st * p.KS, nk = min(p.KS, KCH - kc0);
                     for (int k = 0; k < nk; ++k) {
                         const uint32_t abase = ring_u + s * (uint32_t)p.stage_bytes + (uint32_t)k * chunk_stride;
