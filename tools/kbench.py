@@ -158,7 +158,7 @@ if "colsum" in only:
 if "ew" in only:
     from ddpm_diffusion_model_b200.model.difussion_class import Diffusion, to_image01
     diff = Diffusion(T=1000).to(dev)
-    for (b, s) in [(B, 64), (64, 256)]:
+    for (b, s) in [(B, 64), (64, 256), (160, 256)]:       # 160 x 3 x 256 x 256: 126 MB per fp32 tensor, 380-500 MB working sets (> L2)
         x0 = torch.randn(b, 3, s, s, device=dev); eps = torch.randn_like(x0); z = torch.randn_like(x0)
         t = torch.randint(1, 1000, (b,), device=dev); tp = (t - 10).clamp(min=0)
         n = x0.numel()
