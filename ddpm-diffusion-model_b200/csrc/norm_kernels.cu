@@ -983,7 +983,13 @@ static int gn_max_cluster() {              // experiment: DDPM_B200_GN_CS16=1 al
 static int gn_cluster_size(int HW, int cvs, int N = 1 << 30) {
     const int64_t packets = (int64_t)HW * cvs;
     int cs = 1;
-    while (cs < 8 && packets / (cs * NT) >= 24) cs <<= 1;
+    // DDPM_B200_GN_CSMAX caps the cluster size (experiment knob).  Round 2 measured smaller clusters for the mid-size shapes
+    // (>= 48 packets per thread instead of >= 12): alone, 192@32 backward 82.8 -> 70.7 us, forward 47.3 -> 40.4, 384@16 backward
+    // 46.6 -> 40.1 (profiles/r2_gn_cluster_granularity.txt) -- but in the train step and in DDIM-100 the same-box A/B showed
+    // no change (11.96 vs 12.04 ms; 6.69 vs 6.63 ms per evaluation, inside the noise), so the rule stays as it was.
+    static int cap = 0;
+    if (cap == 0) { const char* e = getenv("DDPM_B200_GN_CSMAX"); cap = e ? atoi(e) : 8; if (cap < 1) cap = 1; }
+    while (cs < 8 && cs < cap && packets / (cs * NT) >= 24) cs <<= 1;
     if (cs == 8 && gn_max_cluster() == 16 && packets / (16 * NT) >= 12) cs = 16;
     // Very few large images (fewer CTAs than SMs with clusters of 8): clusters of 16 (non-portable size) double the number of
     // CTAs per image -- 256-px sampling at B = 16: 12.3 -> 11.5 ms per evaluation; at B = 32 (256 CTAs already) it measured
