@@ -160,6 +160,48 @@ def _get_fused(model, optimizer, arena) -> FusedStep:
     return fs
 
 
+_COPY_STREAMS = {}
+
+
+def _staged_batches(dataloader, dev, max_batches):
+    """Yields the loader's (x, y) pairs with the host->device copy of batch i+1 already in flight on a copy stream while
+    step i computes: `x.to(dev, non_blocking=True)` on the compute stream (train_one_epoch.py:63 of the reference) puts
+    0.25 ms of PCIe time per 6 MB batch in front of every step.  Only pinned CPU tensors are staged ahead (a pageable
+    source blocks the host either way); nothing beyond `max_batches` is drawn from the loader."""
+    key = str(dev)
+    cs = _COPY_STREAMS.get(key)
+    if cs is None:
+        cs = _COPY_STREAMS[key] = torch.cuda.Stream(dev)
+    it = iter(dataloader)
+
+    def stage(i):
+        if (max_batches is not None) and (i >= max_batches):
+            return None
+        try:
+            x, y = next(it)
+        except StopIteration:
+            return None
+        if isinstance(x, torch.Tensor) and x.device.type == "cpu" and x.is_pinned():
+            with torch.cuda.stream(cs):
+                xd = x.to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(cs)
+            return xd, y, ev
+        return x, y, None
+
+    i = 0
+    nxt = stage(0)
+    while nxt is not None:
+        x, y, ev = nxt
+        nxt = stage(i + 1)
+        if ev is not None:
+            cur = torch.cuda.current_stream(dev)
+            cur.wait_event(ev)
+            x.record_stream(cur)
+        yield x, y
+        i += 1
+
+
 def _header(probe_timesteps):
     print("┆   {:>8} | {:>9} | {:>8} | {:>8} | {:>10}{}".format(
         "step", "lr", "loss", "dt(ms)", "grad_norm", (" | probes[t]" if probe_timesteps else "")))
@@ -207,7 +249,7 @@ def train_one_epoch(model, diffusion, dataloader, optimizer, *, scaler=None, ema
         did_header = True
 
     t_loop = time.perf_counter()
-    for i, (x, _) in enumerate(dataloader):
+    for i, (x, _) in enumerate(_staged_batches(dataloader, dev, max_batches)):
         if (max_batches is not None) and (i >= max_batches):
             break
         try:

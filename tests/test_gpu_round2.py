@@ -433,3 +433,41 @@ def test_upsample_folded_into_the_conv_gather(case, monkeypatch):
     monkeypatch.setenv("DDPM_B200_FOLD_UPSAMPLE", "1")
     out3, u = engine.up_fwd(Eg, mod, x, None)
     assert u is not None and rel(out3.interior().float(), out.interior().float()) < 1e-2
+
+
+def test_train_one_epoch_stages_pinned_host_batches_ahead_without_changing_results():
+    """`train_one_epoch` copies batch i+1 from pinned host memory on a copy stream while step i runs (the reference issues
+    `x.to(device, non_blocking=True)` on the compute stream, train_one_epoch.py:63).  Same losses and parameters as with
+    device-resident batches, and the loader is not advanced beyond `max_batches`."""
+    from ddpm_diffusion_model_b200.model.difussion_class import Diffusion
+    from ddpm_diffusion_model_b200.model.unet_backbone import UNetDenoiser
+    from ddpm_diffusion_model_b200.training_loops.train_one_epoch import last_step_losses, train_one_epoch
+
+    def run(host: bool):
+        torch.manual_seed(21)
+        model = UNetDenoiser(3, 32, (1, 2), 1, {8}, 64, 0.0, 2, 16, 16).to(dev())
+        diff = Diffusion(T=50, img_size=16).to(dev())
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-3)
+        g = torch.Generator().manual_seed(3)
+        batches = [torch.randn(4, 3, 16, 16, generator=g) for _ in range(5)]
+        batches = [(b.pin_memory() if host else b.to(dev()), torch.zeros(4)) for b in batches]
+        drawn = []
+
+        def loader():
+            for k, b in enumerate(batches):
+                drawn.append(k)
+                yield b
+        torch.manual_seed(5)                                  # timesteps / noise of loss_simple
+        out = train_one_epoch(model, diff, loader(), opt, scaler=None, ema=None, device="cuda:0", use_autocast=False,
+                              max_batches=3)
+        return out, last_step_losses().clone(), [p.detach().clone() for p in model.parameters()], drawn
+
+    (a_out, a_loss, a_par, a_drawn), (b_out, b_loss, b_par, b_drawn) = run(True), run(False)
+    assert a_out[1:] == b_out[1:] == (3, 12, 3)
+    # (the fp32 CUDA-core gradient kernels accumulate with atomics: equal to rounding, not bit for bit)
+    assert torch.allclose(a_loss, b_loss, rtol=1e-5, atol=0) and abs(a_out[0] - b_out[0]) < 1e-5
+    # parameters: Adam normalises near-zero gradients, so single elements may differ by a step; the tensors agree in norm
+    num = sum(float((p - q).double().pow(2).sum()) for p, q in zip(a_par, b_par))
+    den = sum(float(q.double().pow(2).sum()) for q in b_par)
+    assert (num / den) ** 0.5 < 1e-3
+    assert a_drawn == [0, 1, 2] and b_drawn == [0, 1, 2]

@@ -10,7 +10,7 @@ dev = torch.device("cuda", 0)
 torch.manual_seed(0)
 model = build_unet_64x64(**LOW_GPU).to(dev).eval()
 diff = Diffusion(T=1000, img_size=64).to(dev)
-for B in (8, 64, 256):
+for B in [int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "8,64,256").split(",")]:
     x = torch.randn(B, 3, 64, 64, device=dev)
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
         step = lambda x_, t_, tp_, z_: diff.p_sample_step_ddim(model, x_t=x_, t=t_, t_prev=tp_, eta=0.0, clip_x0=True, noise=z_)
