@@ -7,6 +7,7 @@ per-micro-batch `float(loss)` host sync (train_one_epoch.py:119) becomes a devic
 at the end; under torch.distributed the gradient arena is averaged bucket by bucket during backward.
 """
 import ctypes as C
+import os
 import time
 
 import torch
@@ -161,18 +162,23 @@ def _get_fused(model, optimizer, arena) -> FusedStep:
 
 
 _COPY_STREAMS = {}
+_STAGE_SLOTS = 3
 
 
 def _staged_batches(dataloader, dev, max_batches):
     """Yields the loader's (x, y) pairs with the host->device copy of batch i+1 already in flight on a copy stream while
     step i computes: `x.to(dev, non_blocking=True)` on the compute stream (train_one_epoch.py:63 of the reference) puts
     0.25 ms of PCIe time per 6 MB batch in front of every step.  Only pinned CPU tensors are staged ahead (a pageable
-    source blocks the host either way); nothing beyond `max_batches` is drawn from the loader."""
+    source blocks the host either way); nothing beyond `max_batches` is drawn from the loader.  The device side is a ring
+    of three persistent buffers per batch shape (no allocator traffic, no record_stream): slot k is overwritten only after
+    the compute stream has passed the step that read it."""
     key = str(dev)
-    cs = _COPY_STREAMS.get(key)
-    if cs is None:
-        cs = _COPY_STREAMS[key] = torch.cuda.Stream(dev)
+    st = _COPY_STREAMS.get(key)
+    if st is None:
+        st = _COPY_STREAMS[key] = {"stream": torch.cuda.Stream(dev), "ring": {}}
+    cs, rings = st["stream"], st["ring"]
     it = iter(dataloader)
+    ahead = os.environ.get("DDPM_B200_PREFETCH", "1") != "0"
 
     def stage(i):
         if (max_batches is not None) and (i >= max_batches):
@@ -181,24 +187,37 @@ def _staged_batches(dataloader, dev, max_batches):
             x, y = next(it)
         except StopIteration:
             return None
-        if isinstance(x, torch.Tensor) and x.device.type == "cpu" and x.is_pinned():
+        if ahead and isinstance(x, torch.Tensor) and x.device.type == "cpu" and x.is_pinned():
+            rk = (tuple(x.shape), x.dtype)
+            ring = rings.get(rk)
+            if ring is None:
+                if len(rings) > 4:
+                    rings.clear()
+                ring = rings[rk] = {"buf": [torch.empty(x.shape, dtype=x.dtype, device=dev) for _ in range(_STAGE_SLOTS)],
+                                    "free": [None] * _STAGE_SLOTS, "n": 0}
+            k = ring["n"] % _STAGE_SLOTS
+            ring["n"] += 1
+            if ring["free"][k] is not None:
+                cs.wait_event(ring["free"][k])            # the step that read this slot has been passed by the compute stream
             with torch.cuda.stream(cs):
-                xd = x.to(dev, non_blocking=True)
+                ring["buf"][k].copy_(x, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(cs)
-            return xd, y, ev
-        return x, y, None
+            return ring["buf"][k], y, ev, (ring, k)
+        return x, y, None, None
 
     i = 0
     nxt = stage(0)
     while nxt is not None:
-        x, y, ev = nxt
+        x, y, ev, slot = nxt
         nxt = stage(i + 1)
         if ev is not None:
-            cur = torch.cuda.current_stream(dev)
-            cur.wait_event(ev)
-            x.record_stream(cur)
+            torch.cuda.current_stream(dev).wait_event(ev)
         yield x, y
+        if slot is not None:                                  # everything that reads x has been enqueued by now
+            done = torch.cuda.Event()
+            done.record(torch.cuda.current_stream(dev))
+            slot[0]["free"][slot[1]] = done
         i += 1
 
 
