@@ -231,7 +231,7 @@ def run_ours(args):
     import torch.distributed as dist
     from ddpm_diffusion_model_b200 import _lib
     from ddpm_diffusion_model_b200 import engine as _engine
-    from ddpm_diffusion_model_b200.training_loops.train_one_epoch import last_enqueue_ms_per_step, last_step_losses, train_one_epoch
+    from ddpm_diffusion_model_b200.training_loops.train_one_epoch import last_enqueue_ms_per_step, last_graph_steps, last_step_losses, train_one_epoch
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -311,6 +311,7 @@ def run_ours(args):
     with ClockSampler(local) as clk:
         sec, launches, last, host_s = timed(step_resident, args.steps)
     enqueue_ms = last_enqueue_ms_per_step()           # host loop time per step, excluding the final synchronising loss read
+    graph_steps = last_graph_steps()                  # timed steps that ran as ONE CUDA-graph replay each (train_one_epoch._GraphStep)
     pool_misses = _engine.POOL.misses - miss0
     # ... which includes back-pressure once the launch queue is full (the GPU is the bottleneck at this batch).  The host's own
     # cost per step is what the same loop takes when the GPU is NOT the limit: the same epoch on two-image batches.
@@ -464,7 +465,7 @@ def run_ours(args):
                                                "gather+ToTensor+Normalize kernel per step)"},
                     "sync_every_step": {"value": world * B / sec_sync, "ms_per_step": sec_sync * 1e3,
                                         "timed": "one train_one_epoch call PER step (host reads the loss after every step)"}},
-            "gpu_launches": launches, "host_enqueue_ms_per_step": enqueue_ms, "host_enqueue_ms_per_step_unloaded": enqueue_unloaded_ms,
+            "gpu_launches": launches, "cuda_graph_steps": graph_steps, "host_enqueue_ms_per_step": enqueue_ms, "host_enqueue_ms_per_step_unloaded": enqueue_unloaded_ms,
             "clocks": clk.summary(), "roofline": roof, "cpu_baseline": cpu,
             "loss": last[0] if last else None, "pool_misses_in_timed_region": pool_misses, "ddim100": ddim,
             "train_tflops_per_gpu": gf_train * 1e9 * B * args.steps / sec / 1e12,

@@ -67,6 +67,7 @@ SIGNATURES = {
     "ddpm_abi_version": [],
     "ddpm_num_sms": [_i, C.POINTER(C.c_int)],
     "ddpm_launch_count": [_i],
+    "ddpm_launch_count_add": [_i64],
     "ddpm_schedule_create": [_vp, _i, _i, C.POINTER(_vp)],
     "ddpm_schedule_destroy": [_vp],
     "ddpm_q_sample": [_vp, _vp, _vp, _vp, _vp, _i, _i64, _vp],

@@ -52,6 +52,7 @@ extern "C" int64_t ddpm_launch_count(int reset) {
     if (reset) g_ddpm_launches = 0;
     return v;
 }
+extern "C" int ddpm_launch_count_add(int64_t n) { g_ddpm_launches += n; return 0; }
 
 extern "C" int ddpm_schedule_create(const float* tables_dev, int T, int device, void** handle) {
     if (!tables_dev || !handle || T <= 0 || device < 0 || device >= 64) return DDPM_E_ARG;

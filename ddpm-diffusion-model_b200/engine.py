@@ -55,8 +55,12 @@ class _Pool:
 
     def clear(self):
         self.free.clear()
+        GRAPH_EPOCH[0] += 1       # captured CUDA graphs hold raw addresses of pooled buffers: never replay them after this
 
 
+# Bumped whenever memory that a captured train-step graph may reference by address is released (pool cleared, split-K
+# workspace re-allocated); `train_one_epoch` keys its graphs on it.
+GRAPH_EPOCH = [0]
 POOL = _Pool()
 
 
@@ -251,6 +255,7 @@ class Exec:
         if ws is None or ws.numel() < nbytes:
             ws = torch.empty(max(nbytes, 32 << 20), dtype=torch.uint8, device=self.device)
             _WORKSPACES[key] = ws
+            GRAPH_EPOCH[0] += 1
         return ws
 
     def vec(self, t: torch.Tensor, B: int, Cn: int) -> Act:

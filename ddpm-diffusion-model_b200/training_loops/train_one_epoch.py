@@ -15,7 +15,7 @@ import torch
 from .. import _lib
 from .. import dist as _dist
 from ..arena import ensure_arena
-from ..engine import GLOBAL_WCACHE
+from ..engine import GLOBAL_WCACHE, GRAPH_EPOCH, POOL
 from .ema import EMA  # noqa: F401
 from .grad_scaler import autocast_ctx, make_grad_scaler  # noqa: F401
 from .training_utils import compute_grad_norm, gpu_mem_mb
@@ -44,6 +44,18 @@ class _LossTrace:
         self.chunks[c][k].copy_(loss, non_blocking=True)
         self.n += 1
 
+    def extend(self, vals: torch.Tensor):
+        """Append a 1-D device tensor of per-step losses (the graph step's device ring), stream-ordered, no host sync."""
+        k0 = 0
+        while k0 < vals.numel():
+            c, k = divmod(self.n, self.CHUNK)
+            if c == len(self.chunks):
+                self.chunks.append(torch.empty(self.CHUNK, dtype=torch.float32).pin_memory())
+            m = min(self.CHUNK - k, vals.numel() - k0)
+            self.chunks[c][k:k + m].copy_(vals[k0:k0 + m], non_blocking=True)
+            self.n += m
+            k0 += m
+
     def values(self) -> torch.Tensor:
         if self.n == 0:
             return torch.empty(0)
@@ -53,13 +65,18 @@ class _LossTrace:
 _TRACE = _LossTrace()
 
 
-_ENQUEUE = {"seconds": 0.0, "batches": 0}
+_ENQUEUE = {"seconds": 0.0, "batches": 0, "graph_steps": 0}
 
 
 def last_enqueue_ms_per_step() -> float:
     """Host time the most recent `train_one_epoch` call spent ENQUEUING one micro-batch (loop body only, before the one
     synchronising read of the loss sum at the end): the number that must stay below the GPU time of a step."""
     return 1e3 * _ENQUEUE["seconds"] / max(1, _ENQUEUE["batches"])
+
+
+def last_graph_steps() -> int:
+    """How many micro-batches of the most recent `train_one_epoch` call ran as one CUDA-graph replay each."""
+    return int(_ENQUEUE.get("graph_steps", 0))
 
 
 def last_step_losses() -> torch.Tensor:
@@ -221,6 +238,118 @@ def _staged_batches(dataloader, dev, max_batches):
         i += 1
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# The whole optimiser step as ONE CUDA graph (reference loop body train_one_epoch.py:61-121).
+# Eager, a step is ~300 kernel launches enqueued by ~6.4 ms of host work with ~240 inter-kernel gaps of ~2 us; captured
+# (timestep draw, q_sample, UNet forward + backward incl. the side-stream weight gradients, the fused unscale / clip /
+# AdamW / EMA / scaler pass, the weight repack and the gradient zeroing) it replays with 0.02 ms of host work:
+# 12.00 -> 11.66 ms per step at B = 128 (tools/train_graph_probe.py).  Everything the step mutates lives at fixed device
+# addresses (parameter / gradient / moment / EMA arenas, scaler scale, dropout RNG state, pooled activations); the batch
+# is copied into a static input buffer, the loss goes to a device ring that is drained without a host sync, torch's CUDA
+# generator is graph-safe (`randint` / `randn_like` advance their Philox offset per replay).
+# Used when the step is a pure function of device state: single process, no gradient accumulation, constant
+# hyper-parameters, fused optimiser, no overrides or hooks on the model / diffusion objects; a configuration runs eagerly
+# until an epoch call has ended with at least two steps of it behind (lazy initialisation, pools), then it is captured.  Any change of configuration re-captures; DDPM_B200_TRAIN_GRAPH=0 turns it off.
+# ------------------------------------------------------------------------------------------------------------------
+class _GraphStep:
+    RING = 1024
+
+    def __init__(self, key, x: torch.Tensor):
+        dev = x.device
+        self.key = key
+        self.x = torch.empty_like(x, memory_format=torch.contiguous_format)
+        self.loss_sum = torch.zeros((), dtype=torch.float32, device=dev)
+        self.step_loss = torch.zeros((), dtype=torch.float32, device=dev)
+        self.ring = torch.zeros(self.RING, dtype=torch.float32, device=dev)
+        self.idx = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.pending = 0                                  # ring entries not yet handed to the loss trace
+        self.pos = 0                                      # host mirror of the device-side ring position
+        self.graph = None
+
+    def capture(self, body):
+        def whole():
+            loss = body(self.x)
+            self.step_loss.copy_(loss)
+            self.loss_sum.add_(self.step_loss)
+            self.ring.index_copy_(0, self.idx, self.step_loss.reshape(1))
+            self.idx.add_(1).remainder_(self.RING)
+        g = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count(reset=False)
+        # The graph bakes the ADDRESSES of the pooled activation buffers it was captured with.  Record them and take them out of
+        # the shared pool afterwards: eager work (a forward whose activations are still saved for a backward, a sampler) must
+        # never be handed a buffer that a replay overwrites.
+        used, orig_get = [], POOL.get
+
+        def _recording_get(key, device):
+            t = orig_get(key, device)
+            used.append((key, t))
+            return t
+        POOL.get = _recording_get
+        try:
+            with torch.cuda.graph(g, capture_error_mode=os.environ.get("DDPM_B200_GRAPH_CAPTURE_MODE", "global")):
+                whole()
+        finally:
+            del POOL.get                                  # back to the class method
+        self.n_launch = _lib.launch_count(reset=False) - n0    # library kernels inside the graph (credited per replay)
+        import gc
+        gc.collect()                                      # activation views caught in reference cycles go back to the pool now
+        self.owned, seen = [], set()
+        for key, t in used:
+            if t.data_ptr() in seen:
+                continue
+            seen.add(t.data_ptr())
+            lst = POOL.free.get(key)
+            if lst:
+                for k, u in enumerate(lst):
+                    if u is t:
+                        lst.pop(k)
+                        break
+            self.owned.append(t)
+        self.graph = g
+
+    def run(self, x: torch.Tensor):
+        self.x.copy_(x, non_blocking=True)
+        self.graph.replay()
+        _lib.lib.ddpm_launch_count_add(self.n_launch)
+        self.pos = (self.pos + 1) % self.RING
+        self.pending += 1
+        if self.pending == self.RING:
+            self.drain()
+
+    def drain(self):
+        """Hand the ring entries [pos - pending, pos) (modulo RING, oldest first) to the loss trace; stream-ordered."""
+        if self.pending:
+            lo = (self.pos - self.pending) % self.RING
+            if lo < self.pos:
+                _TRACE.extend(self.ring[lo:self.pos])
+            else:
+                _TRACE.extend(self.ring[lo:])
+                if self.pos:
+                    _TRACE.extend(self.ring[:self.pos])
+            self.pending = 0
+
+
+def _graph_enabled() -> bool:
+    return os.environ.get("DDPM_B200_TRAIN_GRAPH", "1") != "0"
+
+
+def _pure_step(model, diffusion) -> bool:
+    """A captured step replays device work only: it is valid when `diffusion.sample_timesteps`, `diffusion.loss_simple` and
+    `model.forward` are this package's own methods (which draw from torch's CUDA generator and launch kernels) -- not
+    instance-level overrides or hooks, whose host-side effects (a Python iterator feeding noise, logging, ...) a replay
+    would silently skip."""
+    from ..model.difussion_class import Diffusion
+    from ..model.unet_backbone import UNetDenoiser
+    if type(diffusion) is not Diffusion or type(model) is not UNetDenoiser:
+        return False
+    if any(k in vars(diffusion) for k in ("sample_timesteps", "loss_simple", "q_sample")) or "forward" in vars(model):
+        return False
+    for m in model.modules():
+        if m._forward_hooks or m._forward_pre_hooks or m._backward_hooks or getattr(m, "_backward_pre_hooks", None):
+            return False
+    return True
+
+
 def _header(probe_timesteps):
     print("┆   {:>8} | {:>9} | {:>8} | {:>8} | {:>10}{}".format(
         "step", "lr", "loss", "dt(ms)", "grad_norm", (" | probes[t]" if probe_timesteps else "")))
@@ -255,6 +384,19 @@ def train_one_epoch(model, diffusion, dataloader, optimizer, *, scaler=None, ema
 
     loss_sum = torch.zeros((), dtype=torch.float32, device=dev)
     _TRACE.reset()
+    # one-graph-per-step path (see _GraphStep): only when a step is a pure function of device state
+    graph_ok = (_graph_enabled() and world == 1 and grad_accum_steps == 1 and fused.fusable and on_oom == "skip"
+                and not ((base_lr is not None) and (warmup_steps is not None) and (warmup_steps > 0) and global_step < warmup_steps)
+                and not getattr(model, "_ddpm_train_graph_failed", False) and _pure_step(model, diffusion))
+    gcache = getattr(model, "_ddpm_train_graphs", None)   # key -> {"key", "warm", "gs"}; a few configurations stay captured
+    if gcache is None:
+        gcache = {}
+        object.__setattr__(model, "_ddpm_train_graphs", gcache)
+    gstate = None
+    if any(v.get("gs") is not None for v in gcache.values()):
+        GLOBAL_WCACHE.repack_all(_stream(dev))            # parameters may have been changed in place between epochs
+    n_graph_steps = 0
+    last_x = None
     n_seen_batches, n_seen_images = 0, 0
     did_header = False
     if log_every and global_step == 0:
@@ -277,7 +419,6 @@ def train_one_epoch(model, diffusion, dataloader, optimizer, *, scaler=None, ema
             if use_channels_last:
                 x = x.to(memory_format=torch.channels_last)
             B = x.size(0)
-            t = diffusion.sample_timesteps(B, device=dev)
             step_now = ((i + 1) % grad_accum_steps) == 0
             if not arena.grads_attached():
                 arena.attach_grads(zero=True)
@@ -287,15 +428,52 @@ def train_one_epoch(model, diffusion, dataloader, optimizer, *, scaler=None, ema
                 else:
                     sync.reset()
 
-            with autocast_ctx(device="cuda", enabled=bool(use_autocast), dtype="bf16"):
-                loss = diffusion.loss_simple(model, x, t) / grad_accum_steps
-            if use_scaler:
-                scaler.scale(loss).backward()
+            gs = None
+            if graph_ok:
+                g0 = optimizer.param_groups[0]
+                gkey = (GRAPH_EPOCH[0], id(model), id(diffusion), id(optimizer), id(scaler) if use_scaler else None, id(ema), id(fused),
+                        tuple(x.shape), x.dtype, x.is_contiguous(), bool(use_autocast), use_scaler, grad_clip,
+                        float(g0["lr"]), tuple(g0["betas"]), float(g0["eps"]), float(g0["weight_decay"]),
+                        float(ema.decay) if ema is not None else None,
+                        (scaler.get_growth_factor(), scaler.get_backoff_factor(), scaler.get_growth_interval()) if use_scaler else None,
+                        # every buffer the graph reads or writes must still be where it was at capture
+                        arena.flat.data_ptr(), arena.grad.data_ptr(), fused.m.data_ptr(), fused.step.data_ptr(),
+                        scaler._scale.data_ptr() if (use_scaler and scaler._scale is not None) else None,
+                        ema._flat.data_ptr() if (ema is not None and getattr(ema, "_flat", None) is not None) else None)
+                if gstate is None or gstate["key"] != gkey:
+                    if gstate is not None and gstate.get("gs") is not None:
+                        gstate["gs"].drain()
+                        loss_sum += gstate["gs"].loss_sum
+                    gstate = gcache.get(gkey)
+                    if gstate is None:
+                        while len(gcache) >= 4:               # oldest configuration goes (its graph and private pool with it)
+                            gcache.pop(next(iter(gcache)))
+                        gstate = gcache[gkey] = {"key": gkey, "warm": 0, "gs": None}
+                    if gstate["gs"] is not None:
+                        gstate["gs"].loss_sum.zero_()
+                gs = gstate["gs"]
+                last_x = x
+            if gs is not None:
+                gs.run(x)
+                n_graph_steps += 1
+                loss = gs.step_loss
             else:
-                loss.backward()
+                if gstate is not None and graph_ok:
+                    gstate["warm"] += 1
+                t = diffusion.sample_timesteps(B, device=dev)
+                with autocast_ctx(device="cuda", enabled=bool(use_autocast), dtype="bf16"):
+                    loss = diffusion.loss_simple(model, x, t) / grad_accum_steps
+                if use_scaler:
+                    scaler.scale(loss).backward()
+                else:
+                    loss.backward()
 
             gnorm = None
-            if step_now:
+            if gs is not None:
+                if log_grad_norm:
+                    gnorm = fused.grad_norm(scaler, use_scaler)
+                global_step += 1
+            elif step_now:
                 if (base_lr is not None) and (warmup_steps is not None) and (warmup_steps > 0):
                     lr = base_lr * min(1.0, (global_step + 1) / warmup_steps)
                     for g in optimizer.param_groups:
@@ -307,9 +485,10 @@ def train_one_epoch(model, diffusion, dataloader, optimizer, *, scaler=None, ema
                     gnorm = fused.grad_norm(scaler, use_scaler)
                 global_step += 1
 
-            step_loss = loss.detach().float() * grad_accum_steps
-            loss_sum += step_loss
-            _TRACE.push(step_loss)
+            if gs is None:
+                step_loss = loss.detach().float() * grad_accum_steps
+                loss_sum += step_loss
+                _TRACE.push(step_loss)
             n_seen_batches += 1
             n_seen_images += B
 
@@ -353,5 +532,39 @@ def train_one_epoch(model, diffusion, dataloader, optimizer, *, scaler=None, ema
             raise
 
     _ENQUEUE["seconds"], _ENQUEUE["batches"] = time.perf_counter() - t_loop, n_seen_batches
+    _ENQUEUE["graph_steps"] = n_graph_steps
+    if gstate is not None and gstate.get("gs") is not None:
+        gstate["gs"].drain()
+        loss_sum += gstate["gs"].loss_sum
     avg_loss = float(loss_sum.item()) / max(1, n_seen_batches)
+    # Capture for the NEXT call, at a quiet point: the loop is over, the loss read above has synchronised, nothing of the last
+    # iteration is alive.  (Capturing in the middle of the loop was refused by the runtime -- "operation failed due to a previous
+    # error during capture" in every capture-error mode -- while the identical body captured right after an epoch call; the
+    # cost of a capture, ~40 ms, also belongs outside the steps.)
+    if graph_ok and gstate is not None and gstate.get("gs") is None and gstate["warm"] >= 2 and last_x is not None:
+        xs0, Bc = last_x, last_x.size(0)
+        x = loss = None                                   # noqa: F841  (drop the last iteration's tensors)
+
+        def _body(xs):
+            tt = diffusion.sample_timesteps(Bc, device=dev)
+            with autocast_ctx(device="cuda", enabled=bool(use_autocast), dtype="bf16"):
+                ls = diffusion.loss_simple(model, xs, tt)
+            if use_scaler:
+                scaler.scale(ls).backward()
+            else:
+                ls.backward()
+            fused.run(scaler if use_scaler else None, use_scaler, grad_clip, ema)
+            return ls.detach().float()
+        try:
+            arena.attach_grads(zero=True)
+            cand = _GraphStep(gstate["key"], xs0)
+            cand.capture(_body)
+            gstate["gs"] = cand
+        except Exception as ex:                           # an op that cannot be captured: stay eager from now on
+            object.__setattr__(model, "_ddpm_train_graph_failed", True)
+            if verbose:
+                print(f"[ddpm_b200] CUDA-graph capture of the train step failed ({type(ex).__name__}: "
+                      f"{str(ex).splitlines()[0]}); running eagerly")
+            if arena.grad is not None:
+                arena.grad.zero_()
     return avg_loss, n_seen_batches, n_seen_images, global_step

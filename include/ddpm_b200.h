@@ -42,6 +42,9 @@ int ddpm_abi_version(void);
 int ddpm_num_sms(int device, int* out);
 /* Returns and resets the count of kernels this library launched since the last call. */
 int64_t ddpm_launch_count(int reset);
+/* Credits `n` kernel launches to the counter: a CUDA graph captured from these entry points launches the same kernels at
+ * every replay without passing through the library (the host mirror adds the count it observed during capture). */
+int ddpm_launch_count_add(int64_t n);
 /* sizeof() of the six ABI structs in declaration order (ddpm_tensor, ddpm_conv_args, ddpm_lin_entry, ddpm_wgrad_args,
  * ddpm_pack_entry, ddpm_adam_hyper) so that a binding can verify its own layouts when it loads the library (the Python
  * mirror refuses to import on a mismatch).  Returns the number of entries written (<= n). */

@@ -471,3 +471,52 @@ def test_train_one_epoch_stages_pinned_host_batches_ahead_without_changing_resul
     den = sum(float(q.double().pow(2).sum()) for q in b_par)
     assert (num / den) ** 0.5 < 1e-3
     assert a_drawn == [0, 1, 2] and b_drawn == [0, 1, 2]
+
+
+def test_train_step_as_cuda_graph_follows_the_eager_trajectory(monkeypatch):
+    """The optimiser step captured as ONE CUDA graph (train_one_epoch._GraphStep) against the eager loop on the same seeds:
+    the graph draws its timesteps / noise from the same generator sequence, so the per-step losses must track the eager ones
+    (bf16 autocast + GradScaler + AdamW + EMA + clip + dropout), the loss trace is complete and ordered, the optimiser's
+    step counter advances, and a second epoch replays from its first batch."""
+    from ddpm_diffusion_model_b200.model.difussion_class import Diffusion
+    from ddpm_diffusion_model_b200.model.unet_backbone import UNetDenoiser
+    from ddpm_diffusion_model_b200.training_loops.ema import EMA
+    from ddpm_diffusion_model_b200.training_loops.grad_scaler import make_grad_scaler
+    from ddpm_diffusion_model_b200.training_loops import train_one_epoch as T
+
+    def run(flag: str):
+        monkeypatch.setenv("DDPM_B200_TRAIN_GRAPH", flag)
+        torch.manual_seed(31)
+        model = UNetDenoiser(3, 32, (1, 2), 1, {8}, 64, 0.1, 2, 16, 16).to(dev())
+        diff = Diffusion(T=100, img_size=16).to(dev())
+        opt = torch.optim.AdamW(model.parameters(), lr=5e-4, weight_decay=0.01)
+        ema = EMA(model, decay=0.99)
+        scaler = make_grad_scaler("cuda", True)
+        g = torch.Generator().manual_seed(9)
+        batches = [(torch.randn(8, 3, 16, 16, generator=g).to(dev()), torch.zeros(8)) for _ in range(8)]
+        torch.manual_seed(77)
+        out1 = T.train_one_epoch(model, diff, batches, opt, scaler=scaler, ema=ema, device="cuda:0", grad_clip=1.0)
+        tr1, n1 = T.last_step_losses().clone(), T.last_graph_steps()
+        out2 = T.train_one_epoch(model, diff, batches[:5], opt, scaler=scaler, ema=ema, device="cuda:0", grad_clip=1.0, global_step=out1[3])
+        tr2, n2 = T.last_step_losses().clone(), T.last_graph_steps()
+        step = float(opt.state[next(iter(model.parameters()))]["step"])
+        flat = torch.cat([p.detach().float().reshape(-1) for p in model.parameters()])
+        shadow = torch.cat([s.detach().float().reshape(-1) for s in ema.shadow])
+        return out1, tr1, n1, out2, tr2, n2, step, flat, shadow
+
+    e = run("0")
+    e2 = run("0")                                         # eager twice: the run-to-run spread (fp32 atomics in the GroupNorm
+    g = run("1")                                          # parameter gradients) that the graph run is allowed
+    assert e[2] == 0 and e[5] == 0
+    assert g[2] == 0 and g[5] == 5                       # epoch 1 runs eagerly and captures at its end; epoch 2: five replays
+    assert g[1].numel() == 8 and g[4].numel() == 5 and e[1].numel() == 8
+    assert g[0][1:] == e[0][1:] == (8, 64, 8) and g[3][3] == e[3][3] == 13
+    assert e[6] == g[6] == 13.0
+    # same RNG sequence => the losses agree step by step (a different timestep / noise draw moves a loss by tens of percent)
+    assert torch.allclose(g[1], e[1], rtol=2e-2, atol=2e-3), (g[1], e[1])
+    assert torch.allclose(g[4], e[4], rtol=5e-2, atol=5e-3), (g[4], e[4])
+    assert abs(g[0][0] - float(g[1].mean())) < 1e-5 and abs(g[3][0] - float(g[4].mean())) < 1e-5
+    spread_p = float((e2[7] - e[7]).norm() / e[7].norm())
+    spread_s = float((e2[8] - e[8]).norm() / e[8].norm())
+    assert float((g[7] - e[7]).norm() / e[7].norm()) < max(3 * spread_p, 1e-3), spread_p
+    assert float((g[8] - e[8]).norm() / e[8].norm()) < max(3 * spread_s, 1e-4), spread_s
