@@ -391,3 +391,32 @@ def test_reference_arm_runs_the_reference_and_never_imports_the_product():
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["config"]["reference_tree"] != "unknown"
     chk = json.loads([ln for ln in out.stderr.splitlines() if ln.startswith("CHECK ")][-1][6:])
     assert chk == {"bad": [], "so": False}, chk
+
+
+def test_graph_step_is_only_used_for_pure_steps():
+    """train_one_epoch replays a captured CUDA graph only when the step has no host-side effects a replay would skip:
+    this package's own Diffusion / UNetDenoiser methods, no instance-level overrides, no hooks (host logic, no GPU needed)."""
+    import torch
+    from ddpm_diffusion_model_b200.model.difussion_class import Diffusion
+    from ddpm_diffusion_model_b200.model.unet_backbone import UNetDenoiser
+    from ddpm_diffusion_model_b200.training_loops.train_one_epoch import _pure_step
+
+    model = UNetDenoiser(3, 32, (1, 2), 1, {8}, 64, 0.0, 2, 16, 16)
+    diff = Diffusion(T=10, img_size=16)
+    assert _pure_step(model, diff)
+    # a test / user that feeds its own timesteps or noise through an instance attribute: every step must run eagerly
+    diff.sample_timesteps = lambda B, device=None: torch.zeros(B, dtype=torch.long)
+    assert not _pure_step(model, diff)
+    del diff.sample_timesteps
+    assert _pure_step(model, diff)
+    h = model.in_conv.register_forward_hook(lambda m, i, o: None)
+    assert not _pure_step(model, diff)
+    h.remove()
+    assert _pure_step(model, diff)
+    model.forward = lambda x, t: x
+    assert not _pure_step(model, diff)
+    del model.forward
+
+    class Sub(UNetDenoiser):
+        pass
+    assert not _pure_step(Sub(3, 32, (1, 2), 1, {8}, 64, 0.0, 2, 16, 16), diff)
