@@ -458,8 +458,9 @@ def run_ours(args):
                        "l2": "working set per step (~3 GB of activations) exceeds the 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e, "unit": "img/s", "h2d_bytes_per_step": B * 3 * IMG * IMG * 4, "d2h_bytes_per_step": 4,
                     "ms_per_step": sec_e2e / args.steps * 1e3,
-                    "timed": "one train_one_epoch call over K pinned host batches: H2D of the batch (copy stream, one step ahead) and D2H of the step loss "
-                             "(pinned trace) every step, one synchronising read of the mean loss at the end",
+                    "timed": "one train_one_epoch call over K pinned host batches, all inside the timed region: H2D of every batch (copy stream, one "
+                             "step ahead); every step's loss DMA'd to the pinned trace (eager steps: 4 B per step as they finish; CUDA-graph "
+                             "steps: from the device ring in one copy when the epoch ends); one synchronising read of the mean loss at the end",
                     "device_feeder": {"value": world * B * args.steps / sec_feed, "ms_per_step": sec_feed / args.steps * 1e3,
                                       "timed": "same epoch fed by DeviceLoader (uint8 dataset resident in HBM, shuffled; one "
                                                "gather+ToTensor+Normalize kernel per step)"},
