@@ -437,7 +437,7 @@ def train_one_epoch(model, diffusion, dataloader, optimizer, *, scaler=None, ema
                 gkey = (GRAPH_EPOCH[0], id(model), id(diffusion), id(optimizer), id(scaler) if use_scaler else None, id(ema), id(fused),
                         tuple(x.shape), x.dtype, x.is_contiguous(), bool(use_autocast), use_scaler, grad_clip,
                         float(g0["lr"]), tuple(g0["betas"]), float(g0["eps"]), float(g0["weight_decay"]),
-                        float(ema.decay) if ema is not None else None,
+                        float(getattr(ema, "decay", 0.0)) if ema is not None else None,
                         (scaler.get_growth_factor(), scaler.get_backoff_factor(), scaler.get_growth_interval()) if use_scaler else None,
                         # every buffer the graph reads or writes must still be where it was at capture
                         arena.flat.data_ptr(), arena.grad.data_ptr(), fused.m.data_ptr(), fused.step.data_ptr(),
