@@ -458,6 +458,7 @@ def train_one_epoch(model, diffusion, dataloader, optimizer, *, scaler=None, ema
                 last_x = x
             if gs is not None:
                 gs.run(x)
+                gstate["replays"] = gstate.get("replays", 0) + 1
                 n_graph_steps += 1
                 loss = gs.step_loss
             else:
@@ -563,10 +564,22 @@ def train_one_epoch(model, diffusion, dataloader, optimizer, *, scaler=None, ema
             fused.run(scaler if use_scaler else None, use_scaler, grad_clip, ema)
             return ls.detach().float()
         try:
+            # A configuration that changes every epoch (a per-epoch lr schedule bakes a new lr into the key) would be captured
+            # again and again without ever being replayed, each capture holding its own activation buffers: after two captured
+            # graphs that were never replayed the model stays eager; at most two captured configurations are kept.
+            captured = [v for v in gcache.values() if v.get("gs") is not None]
+            if sum(1 for v in captured if v.get("replays", 0) == 0) >= 2:
+                for v in captured:
+                    if v.get("replays", 0) == 0:
+                        v["gs"] = None
+                raise RuntimeError("the step's configuration changes from call to call (captured graphs were never replayed)")
+            for v in captured[:max(0, len(captured) - 1)]:
+                v["gs"] = None
             arena.attach_grads(zero=True)
             cand = _GraphStep(gstate["key"], xs0)
             cand.capture(_body)
             gstate["gs"] = cand
+            gstate["replays"] = 0
         except Exception as ex:                           # an op that cannot be captured: stay eager from now on
             object.__setattr__(model, "_ddpm_train_graph_failed", True)
             if verbose:
